@@ -1,0 +1,843 @@
+// cvr_abi.cu -- implementation of include/cvr_abi.h (libcvr_b200.so).
+//
+// The handle plays the role of the reference's VolPTKernelLauncher<DeviceScene>
+// (RenderKernelLauncher.h:54-73) plus the device half of CudaVolPath
+// (CudaVolPath.cpp): it owns the device volume (cell layouts), the path queue head,
+// the counters and a stream; the caller owns the output buffer.  There is no CPU
+// fallback: every entry point that needs the GPU fails with a message when CUDA does.
+#include "../../include/cvr_abi.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cvr_kernels.cuh"
+
+using namespace cvr;
+
+namespace {
+
+enum Variant { VAR_NAIVE = 0, VAR_REGEN = 1, VAR_STREAM = 2 };
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct cvr_renderer {
+  int device = 0;
+  int variant = VAR_REGEN;
+  std::string kernel_name;
+  std::string err;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+
+  // options
+  int rng_mode = RNG_XORWOW_PATH;
+  int layout = LAYOUT_CELL8;
+  int exact = 1;
+  int rr = 1;
+  uint32_t max_bounces = 1u << 20;
+  int block = CVR_BLOCK;
+  int blocks_per_sm = 0;  // 0 = occupancy query
+  int loop_threshold = 8;
+  int counters = 1;
+
+  // launcher state
+  KernelParams P{};
+  bool scene_set = false;
+  uint32_t tile_w = 0, tile_h = 0;
+  uint32_t iterations = 1;
+  uint32_t seed = 0;
+  uint32_t sample_first = 0, sample_count = 0;
+  float4* d_out = nullptr;
+
+  // device memory owned by the handle
+  float* d_density = nullptr;
+  float* d_dcells = nullptr;
+  float4* d_albedo = nullptr;
+  float4* d_acells = nullptr;
+  unsigned long long* d_head = nullptr;
+  DeviceCounters* d_ctr = nullptr;
+  bool allocated = false;
+
+  // render_image scratch
+  float4* d_tile = nullptr;
+  size_t d_tile_px = 0;
+  float4* d_image = nullptr;
+  size_t d_image_px = 0;
+  uint2* d_origins = nullptr;
+  size_t d_origins_n = 0;
+
+  // launch shape
+  int grid = 0;
+  int regs = 0;
+  bool inited = false;
+
+  // statistics
+  uint64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+  double kernel_ms = 0.0;
+};
+
+namespace {
+
+int fail(cvr_handle h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return 1;
+}
+
+#define CVR_CUDA(h, call)                                                               \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) return fail(h, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define CVR_CHECK_HANDLE(h) \
+  if (!(h)) return fail(nullptr, "null handle")
+
+typedef void (*kernel_fn)(const KernelParams);
+
+kernel_fn pick_kernel(int rng_mode, int layout, int count) {
+#define CVR_K(R, L)                                      \
+  if (rng_mode == R && layout == L)                      \
+    return count ? (kernel_fn)k_volpt<R, L, true> : (kernel_fn)k_volpt<R, L, false>;
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
+  CVR_K(RNG_PHILOX, LAYOUT_CELL8)
+  CVR_K(RNG_PHILOX, LAYOUT_LINEAR)
+#undef CVR_K
+  return nullptr;
+}
+
+int set_device(cvr_handle h) {
+  CVR_CUDA(h, cudaSetDevice(h->device));
+  return 0;
+}
+
+void free_volume(cvr_handle h) {
+  cudaFree(h->d_density);
+  cudaFree(h->d_dcells);
+  cudaFree(h->d_albedo);
+  cudaFree(h->d_acells);
+  h->d_density = h->d_dcells = nullptr;
+  h->d_albedo = h->d_acells = nullptr;
+  h->scene_set = false;
+}
+
+int ensure_allocated(cvr_handle h) {
+  if (h->allocated) return 0;
+  CVR_CUDA(h, cudaMalloc(&h->d_head, sizeof(unsigned long long)));
+  CVR_CUDA(h, cudaMalloc(&h->d_ctr, sizeof(DeviceCounters)));
+  CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
+  CVR_CUDA(h, cudaMemsetAsync(h->d_ctr, 0, sizeof(DeviceCounters), h->stream));
+  h->allocated = true;
+  return 0;
+}
+
+int ensure_init(cvr_handle h) {
+  if (h->inited) return 0;
+  kernel_fn k = pick_kernel(h->rng_mode, h->layout, h->counters);
+  if (!k) return fail(h, "no kernel for rng=%d layout=%d", h->rng_mode, h->layout);
+  cudaFuncAttributes fa;
+  CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
+  h->regs = fa.numRegs;
+  int per_sm = 0;
+  CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, h->block, 0));
+  if (per_sm < 1) return fail(h, "kernel does not fit an SM at block size %d", h->block);
+  if (h->blocks_per_sm > 0 && h->blocks_per_sm < per_sm) per_sm = h->blocks_per_sm;
+  h->grid = per_sm * h->sm_count;
+  h->inited = true;
+  return 0;
+}
+
+void collect_timing(cvr_handle h) {
+  for (auto& ev : h->timing) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess)
+      h->kernel_ms += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  h->timing.clear();
+}
+
+// fills the per-launch part of the kernel parameters and launches
+int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const uint2* origins,
+           uint32_t n_launch_tiles, uint32_t tile_first, uint32_t tile_stride, uint32_t seed,
+           uint32_t seed_step, float4* per_path, unsigned long long path_begin,
+           unsigned long long path_end) {
+  if (!h->scene_set) return fail(h, "launch before cvr_set_scene");
+  if (h->tile_w == 0 || h->tile_h == 0) return fail(h, "launch before cvr_set_resolution");
+  if (set_device(h)) return 1;
+  if (ensure_allocated(h) || ensure_init(h)) return 1;
+  KernelParams& P = h->P;
+  P.npix = (uint32_t)(P.cam.res_x * P.cam.res_y);  // (uint)(c_resolution.x * c_resolution.y)
+  P.tile_w = (uint32_t)P.cam.res_x;
+  P.path_begin = path_begin;
+  P.path_end = path_end;
+  P.tile_origins = origins;
+  P.n_launch_tiles = n_launch_tiles;
+  P.tile_first = tile_first;
+  P.tile_stride = tile_stride;
+  P.seed = seed;
+  P.seed_step = seed_step;
+  P.out = out;
+  P.out_stride = out_stride;
+  P.out_full = out_full;
+  P.per_path = per_path;
+  P.head = h->d_head;
+  P.ctr = h->d_ctr;
+  P.max_bounces = h->max_bounces;
+  P.loop_threshold = h->loop_threshold;
+  P.rr = h->rr;
+  P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
+  P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
+  CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
+  kernel_fn k = pick_kernel(h->rng_mode, h->layout, h->counters);
+  cudaEvent_t e0, e1;
+  CVR_CUDA(h, cudaEventCreate(&e0));
+  CVR_CUDA(h, cudaEventCreate(&e1));
+  CVR_CUDA(h, cudaEventRecord(e0, h->stream));
+  k<<<h->grid, h->block, 0, h->stream>>>(P);
+  CVR_CUDA(h, cudaGetLastError());
+  CVR_CUDA(h, cudaEventRecord(e1, h->stream));
+  h->timing.emplace_back(e0, e1);
+  if (h->timing.size() > 4096) collect_timing(h);
+  h->launches++;
+  return 0;
+}
+
+void path_range(cvr_handle h, unsigned long long& b, unsigned long long& e) {
+  unsigned long long npix = (unsigned long long)(uint32_t)(h->P.cam.res_x * h->P.cam.res_y);
+  uint32_t first = h->sample_first;
+  uint32_t count = h->sample_count ? h->sample_count : (h->iterations - first);
+  if (first > h->iterations) first = h->iterations;
+  if (first + count > h->iterations) count = h->iterations - first;
+  b = npix * first;
+  e = npix * (first + count);
+}
+
+}  // namespace
+
+// =========================================================================== ABI
+extern "C" {
+
+int cvr_abi_version(void) { return CVR_ABI_VERSION; }
+
+const char* cvr_last_error(cvr_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cvr_create(const char* kernel_name, int device, cvr_handle* out) {
+  if (!out) return fail(nullptr, "cvr_create: out is null");
+  *out = nullptr;
+  if (!kernel_name) return fail(nullptr, "cvr_create: kernel name is null");
+  int variant;
+  std::string k(kernel_name);
+  if (k == "naiveSK" || k == "naive")
+    variant = VAR_NAIVE;
+  else if (k == "regenerationSK")
+    variant = VAR_REGEN;
+  else if (k == "streamingSK")
+    variant = VAR_STREAM;
+  else
+    return fail(nullptr,
+                "cvr_create: unknown kernel '%s' (naiveSK | regenerationSK | streamingSK)",
+                kernel_name);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, "cvr_create: no CUDA device (%s); there is no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(nullptr, "cvr_create: device %d of %d", device, n_dev);
+  cvr_handle h = new cvr_renderer();
+  h->device = device;
+  h->variant = variant;
+  h->kernel_name = k;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(nullptr, "cvr_create: cannot create a stream on device %d: %s", device,
+         cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return 1;
+  }
+  h->stream = h->own_stream;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    fail(nullptr, "cvr_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+         prop.major, prop.minor);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 1;
+  }
+  // reference defaults
+  h->P.med.hg_g = 0.f;
+  h->P.med.alpha_x = h->P.med.alpha_y = 0.1f;
+  h->P.med.eta = 1.05f / 1.01f;
+  // naiveSK: Rng(tid) with no seed (Q7); streams are per path by construction
+  *out = h;
+  return 0;
+}
+
+int cvr_release(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  cudaStreamSynchronize(h->stream);
+  collect_timing(h);
+  free_volume(h);
+  cudaFree(h->d_head);
+  cudaFree(h->d_ctr);
+  cudaFree(h->d_tile);
+  cudaFree(h->d_image);
+  cudaFree(h->d_origins);
+  h->d_head = nullptr, h->d_ctr = nullptr, h->d_tile = nullptr, h->d_image = nullptr;
+  h->d_origins = nullptr;
+  h->d_tile_px = h->d_image_px = h->d_origins_n = 0;
+  h->allocated = false;
+  return 0;
+}
+
+int cvr_destroy(cvr_handle h) {
+  if (!h) return 0;
+  cvr_release(h);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int cvr_set_option(cvr_handle h, const char* key, const char* value) {
+  CVR_CHECK_HANDLE(h);
+  if (!key || !value) return fail(h, "cvr_set_option: null key/value");
+  std::string k(key), v(value);
+  if (k == "rng") {
+    if (v == "xorwow-path" || v == "xorwow")
+      h->rng_mode = RNG_XORWOW_PATH;
+    else if (v == "xorwow-thread")
+      h->rng_mode = RNG_XORWOW_THREAD;
+    else if (v == "philox")
+      h->rng_mode = RNG_PHILOX;
+    else
+      return fail(h, "rng: unknown value '%s'", value);
+    if (h->variant == VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD)
+      return fail(h, "rng=xorwow-thread is not a naiveSK mode (NaiveVolPTsk_kernel.cuh:22 seeds per path)");
+    h->inited = false;
+  } else if (k == "layout") {
+    if (v == "cell8")
+      h->layout = LAYOUT_CELL8;
+    else if (v == "linear")
+      h->layout = LAYOUT_LINEAR;
+    else
+      return fail(h, "layout: unknown value '%s'", value);
+    if (h->scene_set) return fail(h, "layout must be chosen before cvr_set_scene");
+    h->inited = false;
+  } else if (k == "tracking") {
+    if (v != "global") return fail(h, "tracking=%s is not available in this build (global only)", value);
+  } else if (k == "exact") {
+    h->exact = atoi(value);
+    if (!h->exact) return fail(h, "exact=0 (fused arithmetic) is not available in this build");
+  } else if (k == "russian_roulette") {
+    h->rr = atoi(value) ? 1 : 0;
+  } else if (k == "max_bounces") {
+    h->max_bounces = (uint32_t)strtoul(value, nullptr, 10);
+  } else if (k == "block") {
+    int b = atoi(value);
+    if (b < 32 || b > CVR_BLOCK || (b % 32)) return fail(h, "block must be a multiple of 32 in [32,%d]", CVR_BLOCK);
+    h->block = b;
+    h->inited = false;
+  } else if (k == "blocks_per_sm") {
+    h->blocks_per_sm = atoi(value);
+    h->inited = false;
+  } else if (k == "loop_threshold") {
+    int t = atoi(value);
+    if (t < 1) return fail(h, "loop_threshold must be >= 1");
+    h->loop_threshold = t;
+  } else if (k == "counters") {
+    h->counters = atoi(value) ? 1 : 0;
+    h->inited = false;
+  } else {
+    return fail(h, "unknown option '%s'", key);
+  }
+  return 0;
+}
+
+int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
+  CVR_CHECK_HANDLE(h);
+  if (!key || !value || cap == 0) return fail(h, "cvr_get_option: bad arguments");
+  std::string k(key), v;
+  if (k == "rng")
+    v = h->rng_mode == RNG_XORWOW_PATH ? "xorwow-path" : h->rng_mode == RNG_XORWOW_THREAD ? "xorwow-thread" : "philox";
+  else if (k == "layout")
+    v = h->layout == LAYOUT_CELL8 ? "cell8" : "linear";
+  else if (k == "tracking")
+    v = "global";
+  else if (k == "exact")
+    v = std::to_string(h->exact);
+  else if (k == "russian_roulette")
+    v = std::to_string(h->rr);
+  else if (k == "max_bounces")
+    v = std::to_string(h->max_bounces);
+  else if (k == "block")
+    v = std::to_string(h->block);
+  else if (k == "blocks_per_sm")
+    v = std::to_string(h->blocks_per_sm);
+  else if (k == "loop_threshold")
+    v = std::to_string(h->loop_threshold);
+  else if (k == "counters")
+    v = std::to_string(h->counters);
+  else if (k == "kernel")
+    v = h->kernel_name;
+  else
+    return fail(h, "unknown option '%s'", key);
+  snprintf(value, cap, "%s", v.c_str());
+  return 0;
+}
+
+int cvr_set_stream(cvr_handle h, void* cuda_stream) {
+  CVR_CHECK_HANDLE(h);
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
+  CVR_CHECK_HANDLE(h);
+  if (!s || !s->density) return fail(h, "cvr_set_scene: null scene/density");
+  for (int i = 0; i < 3; ++i) {
+    if (s->density_dim[i] < 2) return fail(h, "cvr_set_scene: density dims must be >= 2");
+    if (s->albedo && s->albedo_dim[i] < 2) return fail(h, "cvr_set_scene: albedo dims must be >= 2");
+    if (!(s->box_max[i] > s->box_min[i])) return fail(h, "cvr_set_scene: empty box");
+  }
+  if (!(s->scale > 0.f) || !(s->max_density > 0.f))
+    return fail(h, "cvr_set_scene: scale and max_density must be positive");
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_volume(h);
+  MediumParams& m = h->P.med;
+  m.box_min = V3{s->box_min[0], s->box_min[1], s->box_min[2]};
+  m.box_max = V3{s->box_max[0], s->box_max[1], s->box_max[2]};
+  m.scale = s->scale;
+  m.max_density = s->max_density;
+  m.hg_g = s->hg_g;
+  m.alpha_x = s->ggx_alpha[0] > 0.f ? s->ggx_alpha[0] : 0.1f;
+  m.alpha_y = s->ggx_alpha[1] > 0.f ? s->ggx_alpha[1] : 0.1f;
+  m.eta = s->ggx_eta > 0.f ? s->ggx_eta : 1.05f / 1.01f;
+  m.dnx = s->density_dim[0], m.dny = s->density_dim[1], m.dnz = s->density_dim[2];
+  const cudaMemcpyKind kind = s->density_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  size_t nd = (size_t)m.dnx * m.dny * m.dnz;
+  CVR_CUDA(h, cudaMalloc(&h->d_density, nd * sizeof(float)));
+  CVR_CUDA(h, cudaMemcpyAsync(h->d_density, s->density, nd * sizeof(float), kind, h->stream));
+  const int bt = 256;
+  if (h->layout == LAYOUT_CELL8) {
+    size_t ncell = (size_t)(m.dnx + 1) * (m.dny + 1) * (m.dnz + 1);
+    CVR_CUDA(h, cudaMalloc(&h->d_dcells, ncell * 8 * sizeof(float)));
+    int g = (int)std::min<size_t>((ncell + bt - 1) / bt, (size_t)h->sm_count * 32);
+    k_build_density_cells<<<g, bt, 0, h->stream>>>(h->d_density, m.dnx, m.dny, m.dnz, (float4*)h->d_dcells);
+    CVR_CUDA(h, cudaGetLastError());
+  }
+  m.albedo_const = s->albedo ? 0 : 1;
+  m.albedo_r = s->albedo_const[0], m.albedo_g = s->albedo_const[1], m.albedo_b = s->albedo_const[2];
+  m.anx = m.any = m.anz = 2;
+  if (s->albedo) {
+    m.anx = s->albedo_dim[0], m.any = s->albedo_dim[1], m.anz = s->albedo_dim[2];
+    size_t na = (size_t)m.anx * m.any * m.anz;
+    CVR_CUDA(h, cudaMalloc(&h->d_albedo, na * sizeof(float4)));
+    CVR_CUDA(h, cudaMemcpyAsync(h->d_albedo, s->albedo, na * sizeof(float4), kind, h->stream));
+    if (h->layout == LAYOUT_CELL8) {
+      size_t ncell = (size_t)(m.anx + 1) * (m.any + 1) * (m.anz + 1);
+      CVR_CUDA(h, cudaMalloc(&h->d_acells, ncell * 8 * sizeof(float4)));
+      int g = (int)std::min<size_t>((ncell * 8 + bt - 1) / bt, (size_t)h->sm_count * 32);
+      k_build_albedo_cells<<<g, bt, 0, h->stream>>>(h->d_albedo, m.anx, m.any, m.anz, h->d_acells);
+      CVR_CUDA(h, cudaGetLastError());
+    }
+  }
+  if (h->layout == LAYOUT_CELL8) {
+    // the dense copies are only the source of the cell layouts
+    CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_density);
+    cudaFree(h->d_albedo);
+    h->d_density = nullptr;
+    h->d_albedo = nullptr;
+  }
+  m.density = h->d_density;
+  m.dcells = h->d_dcells;
+  m.albedo = h->d_albedo;
+  m.acells = h->d_acells;
+  h->scene_set = true;
+  return 0;
+}
+
+int cvr_set_resolution(cvr_handle h, uint32_t tile_w, uint32_t tile_h) {
+  CVR_CHECK_HANDLE(h);
+  if (tile_w == 0 || tile_h == 0) return fail(h, "cvr_set_resolution: zero tile");
+  h->tile_w = tile_w, h->tile_h = tile_h;
+  h->P.cam.res_x = (float)tile_w;  // make_float2(resolution.x, resolution.y), RenderKernelLauncher.h:35
+  h->P.cam.res_y = (float)tile_h;
+  return 0;
+}
+
+int cvr_set_pixel_index_range(cvr_handle h, float full_w, float full_h) {
+  CVR_CHECK_HANDLE(h);
+  h->P.cam.range_x = full_w, h->P.cam.range_y = full_h;
+  return 0;
+}
+
+int cvr_set_raster_to_view(cvr_handle h, float x, float y) {
+  CVR_CHECK_HANDLE(h);
+  h->P.cam.rtv_x = x, h->P.cam.rtv_y = y;
+  return 0;
+}
+
+int cvr_set_inv_view_matrix(cvr_handle h, const float m[12]) {
+  CVR_CHECK_HANDLE(h);
+  if (!m) return fail(h, "cvr_set_inv_view_matrix: null");
+  memcpy(h->P.cam.m, m, 12 * sizeof(float));
+  return 0;
+}
+
+int cvr_set_offset(cvr_handle h, uint32_t x, uint32_t y) {
+  CVR_CHECK_HANDLE(h);
+  h->P.off_x = x, h->P.off_y = y;
+  return 0;
+}
+
+int cvr_set_output(cvr_handle h, void* d_output_float4) {
+  CVR_CHECK_HANDLE(h);
+  h->d_out = (float4*)d_output_float4;
+  return 0;
+}
+
+int cvr_set_iterations(cvr_handle h, uint32_t n) {
+  CVR_CHECK_HANDLE(h);
+  if (n == 0) return fail(h, "cvr_set_iterations: zero iterations");
+  h->iterations = n;
+  return 0;
+}
+
+int cvr_get_iterations(cvr_handle h, uint32_t* n) {
+  CVR_CHECK_HANDLE(h);
+  if (n) *n = h->iterations;
+  return 0;
+}
+
+int cvr_set_seed(cvr_handle h, uint32_t seed) {
+  CVR_CHECK_HANDLE(h);
+  h->seed = seed;
+  return 0;
+}
+
+int cvr_get_seed(cvr_handle h, uint32_t* seed) {
+  CVR_CHECK_HANDLE(h);
+  if (seed) *seed = h->seed;
+  return 0;
+}
+
+int cvr_set_sample_range(cvr_handle h, uint32_t first, uint32_t count) {
+  CVR_CHECK_HANDLE(h);
+  h->sample_first = first, h->sample_count = count;
+  return 0;
+}
+
+int cvr_init(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  h->inited = false;
+  return ensure_init(h);
+}
+
+int cvr_allocate(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  return ensure_allocated(h);
+}
+
+int cvr_launch_render(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (!h->d_out) return fail(h, "cvr_launch_render before cvr_set_output");
+  unsigned long long b, e;
+  path_range(h, b, e);
+  // naiveSK seeds with the bare path id (NaiveVolPTsk_kernel.cuh:22, Q7)
+  uint32_t seed = h->variant == VAR_NAIVE ? 0u : h->seed;
+  return launch(h, h->d_out, h->tile_w, 0, nullptr, 1, 0, 0, seed, 0, nullptr, b, e);
+}
+
+int cvr_reset(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  // RenderKernelLauncher.cu:353-361 (regeneration: seed_ += n_paths_), :567-575 (streaming: seed_++)
+  uint32_t n_paths = (uint32_t)(h->P.cam.res_x * h->P.cam.res_y) * h->iterations;
+  if (h->variant == VAR_REGEN) h->seed += n_paths;
+  if (h->variant == VAR_STREAM) h->seed += 1;
+  return 0;
+}
+
+int cvr_sync(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cvr_get_counters(cvr_handle h, cvr_counters* out) {
+  CVR_CHECK_HANDLE(h);
+  if (!out) return fail(h, "cvr_get_counters: null");
+  if (set_device(h)) return 1;
+  memset(out, 0, sizeof *out);
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_timing(h);
+  if (h->allocated) {
+    DeviceCounters c;
+    CVR_CUDA(h, cudaMemcpy(&c, h->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+    out->paths = c.paths, out->bounces = c.bounces, out->density_lookups = c.density_lookups;
+    out->albedo_lookups = c.albedo_lookups, out->escaped = c.escaped;
+    out->speculative_lookups = c.speculative;
+  }
+  out->launches = h->launches;
+  out->kernel_ms = h->kernel_ms;
+  return 0;
+}
+
+int cvr_reset_counters(cvr_handle h) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_timing(h);
+  if (h->allocated) CVR_CUDA(h, cudaMemset(h->d_ctr, 0, sizeof(DeviceCounters)));
+  h->launches = 0;
+  h->kernel_ms = 0.0;
+  return 0;
+}
+
+int cvr_get_launch_shape(cvr_handle h, int* grid, int* block, int* regs) {
+  CVR_CHECK_HANDLE(h);
+  if (set_device(h) || ensure_init(h)) return 1;
+  if (grid) *grid = h->grid;
+  if (block) *block = h->block;
+  if (regs) *regs = h->regs;
+  return 0;
+}
+
+int cvr_resolve_tile(cvr_handle h, const void* d_tile, uint32_t tile_w, uint32_t tile_h, void* d_image,
+                     uint32_t full_w, uint32_t full_h, uint32_t off_x, uint32_t off_y, float scale) {
+  CVR_CHECK_HANDLE(h);
+  if (!d_tile || !d_image) return fail(h, "cvr_resolve_tile: null buffer");
+  if (off_x + tile_w > full_w || off_y + tile_h > full_h) return fail(h, "cvr_resolve_tile: tile outside image");
+  if (set_device(h)) return 1;
+  uint32_t n = tile_w * tile_h;
+  int g = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)h->sm_count * 8);
+  k_resolve_tile<<<g, 256, 0, h->stream>>>((const float4*)d_tile, tile_w, tile_h, tile_w, 0, 0,
+                                           (float4*)d_image, full_w, off_x, off_y, scale);
+  CVR_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cvr_tile_table(uint32_t res_x, uint32_t res_y, uint32_t ntx, uint32_t nty, uint32_t tile_dim[2],
+                   uint32_t* origins) {
+  if (!ntx || !nty || !tile_dim) return 1;
+  // Config.h:70-71: ceil() of an INTEGER division, i.e. floor (Q6)
+  tile_dim[0] = (uint32_t)(int)std::ceil((double)(res_x / ntx));
+  tile_dim[1] = (uint32_t)(int)std::ceil((double)(res_y / nty));
+  if (origins) {
+    for (uint32_t id = 0; id < ntx * nty; ++id) {
+      // CudaVolPath.cpp:15-19
+      origins[2 * id + 0] = tile_dim[0] * (id % ntx);
+      origins[2 * id + 1] = tile_dim[1] * (uint32_t)(int)((float)id / (float)ntx);
+    }
+  }
+  return 0;
+}
+
+int cvr_default_camera(uint32_t res_x, uint32_t res_y, float fov_x, float inv_view[12],
+                       float raster_to_view[2]) {
+  // Camera.h:25-37 (right (1,0,0), up (0,-1,0), view (0,0,-1), position (0,0,100)) laid out
+  // as CudaVolPath.cpp:71-84 does: three rows, translation in the fourth column
+  static const float m[12] = {1, 0, 0, 0, 0, -1, 0, 0, 0, 0, -1, 100.0f};
+  if (inv_view) memcpy(inv_view, m, sizeof m);
+  if (raster_to_view) {
+    float fov_y = ((float)res_y / (float)res_x) * fov_x;  // Camera.h:63-67
+    raster_to_view[0] = tanf(fov_x * CVR_PI / 360.f);     // Camera.h:69-71
+    raster_to_view[1] = tanf(fov_y * CVR_PI / 360.f);
+  }
+  return 0;
+}
+
+int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, void* d_image_out) {
+  CVR_CHECK_HANDLE(h);
+  if (!r) return fail(h, "cvr_render_image: null desc");
+  if (!r->res_x || !r->res_y || !r->n_tiles_x || !r->n_tiles_y || !r->iterations)
+    return fail(h, "cvr_render_image: zero resolution / tiles / iterations");
+  if (r->n_tiles_x > r->res_x || r->n_tiles_y > r->res_y) return fail(h, "cvr_render_image: more tiles than pixels");
+  if (!h->scene_set) return fail(h, "cvr_render_image before cvr_set_scene");
+  if (set_device(h)) return 1;
+  const uint32_t n_tiles = r->n_tiles_x * r->n_tiles_y;
+  std::vector<uint32_t> origins(2 * (size_t)n_tiles);
+  uint32_t tile_dim[2];
+  cvr_tile_table(r->res_x, r->res_y, r->n_tiles_x, r->n_tiles_y, tile_dim, origins.data());
+  float inv_view[12], rtv[2];
+  cvr_default_camera(r->res_x, r->res_y, r->fov_x > 0.f ? r->fov_x : 0.7f, inv_view, rtv);
+  if (r->inv_view) memcpy(inv_view, r->inv_view, sizeof inv_view);
+  if (r->raster_to_view) memcpy(rtv, r->raster_to_view, sizeof rtv);
+  // constructor + render() prologue order of CudaVolPath (CudaVolPath.cpp:39-58, 338-341)
+  cvr_set_raster_to_view(h, rtv[0], rtv[1]);
+  cvr_set_resolution(h, tile_dim[0], tile_dim[1]);
+  cvr_set_pixel_index_range(h, (float)r->res_x, (float)r->res_y);
+  if (ensure_init(h) || ensure_allocated(h)) return 1;
+  cvr_set_iterations(h, r->iterations);
+  cvr_set_inv_view_matrix(h, inv_view);
+  cvr_set_sample_range(h, r->sample_first, r->sample_count);
+
+  const size_t image_px = (size_t)r->res_x * r->res_y;
+  const size_t tile_px = (size_t)tile_dim[0] * tile_dim[1];
+  if (h->d_image_px < image_px) {
+    cudaFree(h->d_image);
+    h->d_image_px = 0;
+    CVR_CUDA(h, cudaMalloc(&h->d_image, image_px * sizeof(float4)));
+    h->d_image_px = image_px;
+  }
+  float4* d_image = d_image_out ? (float4*)d_image_out : h->d_image;
+  const uint32_t stride = r->tile_stride ? r->tile_stride : 1;
+  const uint32_t first = r->tile_first;
+  const uint32_t n_paths_tile = (uint32_t)tile_px * r->iterations;  // uint, RenderKernelLauncher.cu:125
+  // stream base of global tile k = seed0 + k * step, i.e. what reset() accumulates on one GPU
+  const uint32_t seed0 = h->variant == VAR_NAIVE ? 0u : h->seed;
+  const uint32_t seed_step = h->variant == VAR_REGEN ? n_paths_tile : h->variant == VAR_STREAM ? 1u : 0u;
+  unsigned long long pb, pe;
+  path_range(h, pb, pe);
+  const float scale = (float)r->iterations;  // UtilityFunctors::Scale(current_iteration_)
+  const int rg = (int)std::min<size_t>((tile_px + 255) / 256, (size_t)h->sm_count * 8);
+
+  if (r->fuse_tiles) {
+    // one launch over every owned tile, accumulating straight into a full-resolution
+    // buffer; same pixels, same streams as the loop below
+    if (h->d_tile_px < image_px) {
+      cudaFree(h->d_tile);
+      h->d_tile_px = 0;
+      CVR_CUDA(h, cudaMalloc(&h->d_tile, image_px * sizeof(float4)));
+      h->d_tile_px = image_px;
+    }
+    if (h->d_origins_n < n_tiles) {
+      cudaFree(h->d_origins);
+      h->d_origins_n = 0;
+      CVR_CUDA(h, cudaMalloc(&h->d_origins, n_tiles * sizeof(uint2)));
+      h->d_origins_n = n_tiles;
+    }
+    CVR_CUDA(h, cudaMemcpyAsync(h->d_origins, origins.data(), n_tiles * sizeof(uint2),
+                                cudaMemcpyHostToDevice, h->stream));
+    CVR_CUDA(h, cudaMemsetAsync(h->d_tile, 0, image_px * sizeof(float4), h->stream));
+    uint32_t n_mine = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    if (n_mine) {
+      if (launch(h, h->d_tile, r->res_x, 1, h->d_origins, n_mine, first, stride, seed0, seed_step,
+                 nullptr, pb, pe))
+        return 1;
+    }
+    for (uint32_t k = first; k < n_tiles; k += stride) {
+      uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
+      k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, ox, oy,
+                                                d_image, r->res_x, ox, oy, scale);
+    }
+    CVR_CUDA(h, cudaGetLastError());
+  } else {
+    if (h->d_tile_px < tile_px) {
+      cudaFree(h->d_tile);
+      h->d_tile_px = 0;
+      CVR_CUDA(h, cudaMalloc(&h->d_tile, tile_px * sizeof(float4)));
+      h->d_tile_px = tile_px;
+    }
+    for (uint32_t k = first; k < n_tiles; k += stride) {
+      uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
+      // initRenderState / prepareForNextIterations: zeroed tile buffer (CudaVolPath.cpp:188-208)
+      CVR_CUDA(h, cudaMemsetAsync(h->d_tile, 0, tile_px * sizeof(float4), h->stream));
+      cvr_set_offset(h, ox, oy);  // copyOffset (CudaVolPath.cpp:260)
+      if (launch(h, h->d_tile, tile_dim[0], 0, nullptr, 1, 0, 0, seed0 + k * seed_step, 0, nullptr, pb, pe))
+        return 1;
+      k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], tile_dim[0], 0, 0,
+                                                d_image, r->res_x, ox, oy, scale);
+      CVR_CUDA(h, cudaGetLastError());
+    }
+  }
+  if (host_image) {
+    for (uint32_t k = first; k < n_tiles; k += stride) {
+      uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
+      size_t off = (size_t)oy * r->res_x + ox;
+      CVR_CUDA(h, cudaMemcpy2DAsync(host_image + 4 * off, (size_t)r->res_x * sizeof(float4), d_image + off,
+                                    (size_t)r->res_x * sizeof(float4), tile_dim[0] * sizeof(float4),
+                                    tile_dim[1], cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  // what the sequence of reset() calls leaves behind after all tiles
+  h->seed += n_tiles * seed_step;
+  return 0;
+}
+
+int cvr_trace_paths(cvr_handle h, uint64_t first, uint64_t count, void* d_per_path) {
+  CVR_CHECK_HANDLE(h);
+  if (!d_per_path || !count) return fail(h, "cvr_trace_paths: null buffer / zero count");
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaMemsetAsync(d_per_path, 0, count * sizeof(float4), h->stream));
+  uint32_t seed = h->variant == VAR_NAIVE ? 0u : h->seed;
+  return launch(h, nullptr, h->tile_w, 0, nullptr, 1, 0, 0, seed, 0, (float4*)d_per_path, first,
+                first + count);
+}
+
+int cvr_rng_kat(cvr_handle h, const int32_t* seeds, int n_seeds, int n, uint32_t* words, float* uniforms) {
+  CVR_CHECK_HANDLE(h);
+  if (!seeds || n_seeds <= 0 || n <= 0 || !words || !uniforms) return fail(h, "cvr_rng_kat: bad arguments");
+  if (set_device(h)) return 1;
+  int32_t* d_s;
+  uint32_t* d_w;
+  float* d_u;
+  size_t tot = (size_t)n_seeds * n;
+  CVR_CUDA(h, cudaMalloc(&d_s, n_seeds * sizeof(int32_t)));
+  CVR_CUDA(h, cudaMalloc(&d_w, tot * 4));
+  CVR_CUDA(h, cudaMalloc(&d_u, tot * 4));
+  CVR_CUDA(h, cudaMemcpyAsync(d_s, seeds, n_seeds * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  k_rng_kat<<<(n_seeds + 63) / 64, 64, 0, h->stream>>>(d_s, n_seeds, n, d_w, d_u);
+  CVR_CUDA(h, cudaGetLastError());
+  CVR_CUDA(h, cudaMemcpyAsync(words, d_w, tot * 4, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaMemcpyAsync(uniforms, d_u, tot * 4, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_s), cudaFree(d_w), cudaFree(d_u);
+  return 0;
+}
+
+int cvr_debug_lookup(cvr_handle h, const float* p, int n, float* dens, float* alb) {
+  CVR_CHECK_HANDLE(h);
+  if (!h->scene_set) return fail(h, "cvr_debug_lookup before cvr_set_scene");
+  if (!p || n <= 0 || !dens || !alb) return fail(h, "cvr_debug_lookup: bad arguments");
+  if (set_device(h)) return 1;
+  float *d_p, *d_d, *d_a;
+  CVR_CUDA(h, cudaMalloc(&d_p, (size_t)n * 12));
+  CVR_CUDA(h, cudaMalloc(&d_d, (size_t)n * 4));
+  CVR_CUDA(h, cudaMalloc(&d_a, (size_t)n * 12));
+  CVR_CUDA(h, cudaMemcpyAsync(d_p, p, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+  if (h->layout == LAYOUT_CELL8)
+    k_debug_lookup<LAYOUT_CELL8><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, d_p, n, d_d, d_a);
+  else
+    k_debug_lookup<LAYOUT_LINEAR><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, d_p, n, d_d, d_a);
+  CVR_CUDA(h, cudaGetLastError());
+  CVR_CUDA(h, cudaMemcpyAsync(dens, d_d, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaMemcpyAsync(alb, d_a, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_p), cudaFree(d_d), cudaFree(d_a);
+  return 0;
+}
+
+}  // extern "C"

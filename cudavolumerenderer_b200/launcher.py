@@ -1,0 +1,267 @@
+"""Python mirror of the reference's kernel-launcher plugin surface, over the C ABI.
+
+Class and method names follow RenderKernelLauncher / VolPTKernelLauncher
+(reference implementation/src/RenderKernelLauncher.h:20-73) and the three launcher
+classes the hot path covers (:75-82 NaiveVolPTsk, :104-113 RegenerationVolPTsk,
+:139-151 StreamingVolPTsk) so that code written against the reference reads the same.
+Every method is one C-ABI call; errors raise CvrError (the reference exit()s).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import CvrError, Counters, SceneDesc
+
+
+class Scene:
+    """Host-side scene = what SceneAssembler::getScene returns (Scene.h:19-54): a
+    camera (fov / optional matrices) and a HostMedium (Medium.h:109-116,191)."""
+
+    def __init__(self, density: np.ndarray, albedo: np.ndarray | None, box_min, box_max, scale: float,
+                 max_density: float, fov_x: float = 0.7, albedo_const=(1.0, 1.0, 1.0), hg_g: float = 0.0,
+                 ggx_alpha=(0.1, 0.1), ggx_eta: float | None = None, inv_view=None, name: str = "scene"):
+        density = np.ascontiguousarray(density, np.float32)
+        if density.ndim != 3:
+            raise ValueError("density must be (nz, ny, nx)")
+        if albedo is not None:
+            albedo = np.ascontiguousarray(albedo, np.float32)
+            if albedo.ndim != 4 or albedo.shape[3] != 4:
+                raise ValueError("albedo must be (nz, ny, nx, 4)")
+        self.density, self.albedo = density, albedo
+        self.box_min = tuple(float(x) for x in box_min)
+        self.box_max = tuple(float(x) for x in box_max)
+        self.scale, self.max_density = float(scale), float(max_density)
+        self.fov_x = float(fov_x)
+        self.albedo_const = tuple(float(x) for x in albedo_const)
+        self.hg_g = float(hg_g)
+        self.ggx_alpha = tuple(float(x) for x in ggx_alpha)
+        # Bsdf.h:21-22: float(1.05) / float(1.01)
+        self.ggx_eta = float(np.float32(1.05) / np.float32(1.01)) if ggx_eta is None else float(ggx_eta)
+        self.inv_view = None if inv_view is None else np.asarray(inv_view, np.float32).reshape(12)
+        self.name = name
+
+    def desc(self) -> SceneDesc:
+        d = SceneDesc()
+        d.density = self.density.ctypes.data
+        d.density_dim[:] = [self.density.shape[2], self.density.shape[1], self.density.shape[0]]
+        if self.albedo is not None:
+            d.albedo = self.albedo.ctypes.data
+            d.albedo_dim[:] = [self.albedo.shape[2], self.albedo.shape[1], self.albedo.shape[0]]
+        else:
+            d.albedo = None
+        d.albedo_const[:] = self.albedo_const
+        d.box_min[:] = self.box_min
+        d.box_max[:] = self.box_max
+        d.scale, d.max_density, d.hg_g = self.scale, self.max_density, self.hg_g
+        d.ggx_alpha[:] = self.ggx_alpha
+        d.ggx_eta = self.ggx_eta
+        d.density_on_device = 0
+        return d
+
+    @property
+    def volume_bytes(self) -> int:
+        return self.density.nbytes + (self.albedo.nbytes if self.albedo is not None else 0)
+
+
+class VolPTKernelLauncher:
+    """RenderKernelLauncher + VolPTKernelLauncher<DeviceScene> (RenderKernelLauncher.h:20-73)."""
+
+    KERNEL = "regenerationSK"
+
+    def __init__(self, device: int = 0, **options):
+        self._lib = abi.load()
+        h = C.c_void_p()
+        rc = self._lib.cvr_create(self.KERNEL.encode(), device, C.byref(h))
+        if rc:
+            raise CvrError("cvr_create: " + self._lib.cvr_last_error(None).decode())
+        self._h = h
+        self.device = device
+        for k, v in options.items():
+            self.setOption(k, v)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cvr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        abi.check(self._h, rc, what)
+
+    # -- options / stream (new-build additions)
+    def setOption(self, key: str, value) -> None:
+        self._ck(self._lib.cvr_set_option(self._h, key.encode(), str(value).encode()), f"set_option({key})")
+
+    def getOption(self, key: str) -> str:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.cvr_get_option(self._h, key.encode(), buf, 64), f"get_option({key})")
+        return buf.value.decode()
+
+    def setStream(self, cuda_stream_ptr: int | None) -> None:
+        self._ck(self._lib.cvr_set_stream(self._h, cuda_stream_ptr), "set_stream")
+
+    # -- RenderKernelLauncher.h:31-51
+    def setOutputPtr(self, d_output: int) -> None:
+        self._ck(self._lib.cvr_set_output(self._h, d_output), "setOutputPtr")
+
+    def setResolution(self, w: int, h: int) -> None:
+        self._ck(self._lib.cvr_set_resolution(self._h, w, h), "setResolution")
+
+    def copyInvViewMatrix(self, m) -> None:
+        m = np.ascontiguousarray(m, np.float32).reshape(12)
+        self._ck(self._lib.cvr_set_inv_view_matrix(self._h, m.ctypes.data_as(abi.f32p)), "copyInvViewMatrix")
+
+    def copyRasterToView(self, x: float, y: float) -> None:
+        self._ck(self._lib.cvr_set_raster_to_view(self._h, x, y), "copyRasterToView")
+
+    def copyPixelIndexRange(self, w: float, h: float) -> None:
+        self._ck(self._lib.cvr_set_pixel_index_range(self._h, w, h), "copyPixelIndexRange")
+
+    def copyOffset(self, x: int, y: int) -> None:
+        self._ck(self._lib.cvr_set_offset(self._h, x, y), "copyOffset")
+
+    def init(self) -> None:
+        self._ck(self._lib.cvr_init(self._h), "init")
+
+    def allocateDeviceMemory(self) -> None:
+        self._ck(self._lib.cvr_allocate(self._h), "allocateDeviceMemory")
+
+    def launchRender(self) -> None:
+        self._ck(self._lib.cvr_launch_render(self._h), "launchRender")
+
+    def reset(self) -> None:
+        self._ck(self._lib.cvr_reset(self._h), "reset")
+
+    def sync(self) -> None:
+        self._ck(self._lib.cvr_sync(self._h), "sync")
+
+    def releaseDeviceMemory(self) -> None:
+        self._ck(self._lib.cvr_release(self._h), "releaseDeviceMemory")
+
+    # -- VolPTKernelLauncher (RenderKernelLauncher.h:54-73)
+    def setNIterations(self, n: int) -> None:
+        self._ck(self._lib.cvr_set_iterations(self._h, n), "setNIterations")
+
+    def getNIterations(self) -> int:
+        n = C.c_uint32()
+        self._ck(self._lib.cvr_get_iterations(self._h, C.byref(n)), "getNIterations")
+        return n.value
+
+    def setScene(self, scene: Scene) -> None:
+        d = scene.desc()
+        self._ck(self._lib.cvr_set_scene(self._h, C.byref(d)), "setScene")
+        self._scene = scene
+
+    def getScene(self) -> Scene:
+        return self._scene
+
+    # -- seeds / sharding / statistics
+    def setSeed(self, seed: int) -> None:
+        self._ck(self._lib.cvr_set_seed(self._h, seed & 0xffffffff), "setSeed")
+
+    def getSeed(self) -> int:
+        s = C.c_uint32()
+        self._ck(self._lib.cvr_get_seed(self._h, C.byref(s)), "getSeed")
+        return s.value
+
+    def setSampleRange(self, first: int, count: int) -> None:
+        self._ck(self._lib.cvr_set_sample_range(self._h, first, count), "setSampleRange")
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self._lib.cvr_get_counters(self._h, C.byref(c)), "counters")
+        return c.as_dict()
+
+    def resetCounters(self) -> None:
+        self._ck(self._lib.cvr_reset_counters(self._h), "resetCounters")
+
+    def launchShape(self):
+        g, b, r = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.cvr_get_launch_shape(self._h, C.byref(g), C.byref(b), C.byref(r)), "launchShape")
+        return g.value, b.value, r.value
+
+    def resolveTile(self, d_tile: int, tile_w: int, tile_h: int, d_image: int, full_w: int, full_h: int,
+                    off_x: int, off_y: int, scale: float) -> None:
+        self._ck(self._lib.cvr_resolve_tile(self._h, d_tile, tile_w, tile_h, d_image, full_w, full_h,
+                                            off_x, off_y, scale), "resolveTile")
+
+    def renderImage(self, res, n_tiles=(1, 1), iterations: int = 20, fov_x: float = 0.7, inv_view=None,
+                    raster_to_view=None, tile_first: int = 0, tile_stride: int = 1, sample_first: int = 0,
+                    sample_count: int = 0, fuse_tiles: bool = False, host_image: np.ndarray | None = None,
+                    d_image: int | None = None) -> np.ndarray | None:
+        """CudaVolPath::render (CudaVolPath.cpp:338-347) in one C-ABI call."""
+        r = abi.RenderDesc()
+        r.res_x, r.res_y = res
+        r.n_tiles_x, r.n_tiles_y = n_tiles
+        r.iterations, r.fov_x = iterations, fov_x
+        keep = []
+        if inv_view is not None:
+            iv = np.ascontiguousarray(inv_view, np.float32).reshape(12)
+            keep.append(iv)
+            r.inv_view = iv.ctypes.data_as(abi.f32p)
+        if raster_to_view is not None:
+            rv = np.ascontiguousarray(raster_to_view, np.float32).reshape(2)
+            keep.append(rv)
+            r.raster_to_view = rv.ctypes.data_as(abi.f32p)
+        r.tile_first, r.tile_stride = tile_first, tile_stride
+        r.sample_first, r.sample_count = sample_first, sample_count
+        r.fuse_tiles = 1 if fuse_tiles else 0
+        if host_image is None and d_image is None:
+            host_image = np.zeros((res[1], res[0], 4), np.float32)
+        hp = host_image.ctypes.data if host_image is not None else None
+        self._ck(self._lib.cvr_render_image(self._h, C.byref(r), hp, d_image), "renderImage")
+        return host_image
+
+    # -- parity hooks
+    def tracePaths(self, first: int, count: int, d_per_path: int) -> None:
+        self._ck(self._lib.cvr_trace_paths(self._h, first, count, d_per_path), "tracePaths")
+
+    def rngKat(self, seeds, n: int):
+        seeds = np.ascontiguousarray(seeds, np.int32)
+        w = np.zeros((len(seeds), n), np.uint32)
+        u = np.zeros((len(seeds), n), np.float32)
+        self._ck(self._lib.cvr_rng_kat(self._h, seeds.ctypes.data_as(C.POINTER(C.c_int32)), len(seeds), n,
+                                       w.ctypes.data_as(abi.u32p), u.ctypes.data_as(abi.f32p)), "rngKat")
+        return w, u
+
+    def debugLookup(self, p01: np.ndarray):
+        p = np.ascontiguousarray(p01, np.float32).reshape(-1, 3)
+        d = np.zeros(len(p), np.float32)
+        a = np.zeros((len(p), 3), np.float32)
+        self._ck(self._lib.cvr_debug_lookup(self._h, p.ctypes.data_as(abi.f32p), len(p),
+                                            d.ctypes.data_as(abi.f32p), a.ctypes.data_as(abi.f32p)), "debugLookup")
+        return d, a
+
+
+class NaiveVolPTsk(VolPTKernelLauncher):
+    """-k naiveSK (RenderKernelLauncher.h:75-82; NaiveVolPTsk_kernel.cuh)."""
+    KERNEL = "naiveSK"
+
+
+class RegenerationVolPTsk(VolPTKernelLauncher):
+    """-k regenerationSK (RenderKernelLauncher.h:104-113; RegenerationVolPTsk_kernel.cuh:146-232)."""
+    KERNEL = "regenerationSK"
+
+
+class StreamingVolPTsk(VolPTKernelLauncher):
+    """-k streamingSK (RenderKernelLauncher.h:139-151; StreamingVolPTsk_kernel.cuh)."""
+    KERNEL = "streamingSK"
+
+
+KERNELS = {"naiveSK": NaiveVolPTsk, "regenerationSK": RegenerationVolPTsk, "streamingSK": StreamingVolPTsk}
+
+
+def createLauncher(kernel: str, device: int = 0, **options) -> VolPTKernelLauncher:
+    """Config::getKernel + RendererFactory switch (Config.h:228-235, RendererFactory.h:37-115)."""
+    if kernel not in KERNELS:
+        raise ValueError(f"kernel '{kernel}' not available (choices: {sorted(KERNELS)})")
+    return KERNELS[kernel](device, **options)

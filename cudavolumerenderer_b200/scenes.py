@@ -1,0 +1,48 @@
+"""Named scenes of BASELINE.json's configs, as procedural stand-ins.
+
+Every volume payload in the reference checkout is a Git-LFS pointer stub, so the
+scenes are synthesised by libcvr_b200.so (csrc/cvr_synth.cpp) with the grid shapes and
+medium parameters the reference's loaders would produce:
+
+  bucky   RawSceneBuilder.h:35-83     32^3, box +-0.5, scale 40, max_density 1, fov 0.7
+  hetvol  XmlSceneBuilder.h:39-152    density 128x128x50, albedo grid box
+          [-0.64,-0.64,-0.25]..[0.64,0.64,0.25] becomes the medium box (Q3), scale 800,
+          fov 0.33 (data/mitsubaxml/smoke/hetvol.xml)
+  manix   VDBSceneBuilder.h:40-80     256x230x256, box +-0.5, scale 100, fov 0.7
+  fbm     synthetic n^3, constant albedo 0.99, scale 100
+"""
+from __future__ import annotations
+
+from . import abi
+from .launcher import Scene
+
+
+def bucky(seed: int = 0) -> Scene:
+    den, alb, mx = abi.synth_volume("bucky", 32, 32, 32, seed)
+    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=40.0, max_density=mx, fov_x=0.7, name="bucky")
+
+
+def hetvol(seed: int = 0, dims=(128, 128, 50)) -> Scene:
+    den, alb, mx = abi.synth_volume("hetvol", dims[0], dims[1], dims[2], seed)
+    return Scene(den, alb, (-0.64, -0.64, -0.25), (0.64, 0.64, 0.25), scale=800.0, max_density=mx,
+                 fov_x=0.33, name="hetvol")
+
+
+def manix(seed: int = 0, dims=(256, 230, 256)) -> Scene:
+    den, alb, mx = abi.synth_volume("manix", dims[0], dims[1], dims[2], seed)
+    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=mx, fov_x=0.7, name="manix")
+
+
+def fbm(n: int = 256, seed: int = 0, albedo: float = 0.99) -> Scene:
+    den, _, mx = abi.synth_volume("fbm", n, n, n, seed, with_albedo=False)
+    return Scene(den, None, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=mx, fov_x=0.7,
+                 albedo_const=(albedo,) * 3, name=f"fbm{n}")
+
+
+SCENES = {"bucky": bucky, "hetvol": hetvol, "manix": manix, "fbm": fbm}
+
+
+def make(name: str, **kw) -> Scene:
+    if name not in SCENES:
+        raise ValueError(f"unknown scene '{name}' (choices: {sorted(SCENES)})")
+    return SCENES[name](**kw)

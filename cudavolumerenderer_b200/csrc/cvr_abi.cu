@@ -46,8 +46,11 @@ struct cvr_renderer {
   uint32_t max_bounces = 1u << 20;
   int block = CVR_BLOCK;
   int blocks_per_sm = 0;  // 0 = occupancy query
-  int loop_threshold = 8;
+  int loop_threshold = 16;
   int counters = 1;
+  int sched = 1;  // 0 = lane-persistent, 1 = block-sorted wavefront
+  int track_steps = 4;
+  int track_min_lanes = 8;
 
   // launcher state
   KernelParams P{};
@@ -112,9 +115,9 @@ int fail(cvr_handle h, const char* fmt, ...) {
 
 typedef void (*kernel_fn)(const KernelParams);
 
-kernel_fn pick_kernel(int rng_mode, int layout, int count) {
+kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count) {
 #define CVR_K(R, L)                                      \
-  if (rng_mode == R && layout == L)                      \
+  if (sched == 0 && rng_mode == R && layout == L)        \
     return count ? (kernel_fn)k_volpt<R, L, true> : (kernel_fn)k_volpt<R, L, false>;
   CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
   CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
@@ -122,6 +125,14 @@ kernel_fn pick_kernel(int rng_mode, int layout, int count) {
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
   CVR_K(RNG_PHILOX, LAYOUT_CELL8)
   CVR_K(RNG_PHILOX, LAYOUT_LINEAR)
+#undef CVR_K
+#define CVR_K(R, L)                                      \
+  if (sched == 1 && rng_mode == R && layout == L)        \
+    return count ? (kernel_fn)k_volpt_sorted<R, L, true> : (kernel_fn)k_volpt_sorted<R, L, false>;
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
 #undef CVR_K
   return nullptr;
 }
@@ -153,8 +164,8 @@ int ensure_allocated(cvr_handle h) {
 
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->rng_mode, h->layout, h->counters);
-  if (!k) return fail(h, "no kernel for rng=%d layout=%d", h->rng_mode, h->layout);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters);
+  if (!k) return fail(h, "no kernel for sched=%d rng=%d layout=%d (philox needs sched=lane)", h->sched, h->rng_mode, h->layout);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
@@ -207,11 +218,13 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.ctr = h->d_ctr;
   P.max_bounces = h->max_bounces;
   P.loop_threshold = h->loop_threshold;
+  P.track_steps = h->track_steps;
+  P.track_min_lanes = h->track_min_lanes;
   P.rr = h->rr;
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->rng_mode, h->layout, h->counters);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters);
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
@@ -336,6 +349,7 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
       h->rng_mode = RNG_PHILOX;
     else
       return fail(h, "rng: unknown value '%s'", value);
+    if (h->rng_mode == RNG_PHILOX) h->sched = 0;  // the sorted scheduler stores XORWOW state only
     if (h->variant == VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD)
       return fail(h, "rng=xorwow-thread is not a naiveSK mode (NaiveVolPTsk_kernel.cuh:22 seeds per path)");
     h->inited = false;
@@ -369,6 +383,20 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     int t = atoi(value);
     if (t < 1) return fail(h, "loop_threshold must be >= 1");
     h->loop_threshold = t;
+  } else if (k == "sched") {
+    if (v == "lane")
+      h->sched = 0;
+    else if (v == "sorted")
+      h->sched = 1;
+    else
+      return fail(h, "sched: unknown value '%s' (lane | sorted)", value);
+    h->inited = false;
+  } else if (k == "track_steps") {
+    int t = atoi(value);
+    if (t < 1) return fail(h, "track_steps must be >= 1");
+    h->track_steps = t;
+  } else if (k == "track_min_lanes") {
+    h->track_min_lanes = atoi(value);
   } else if (k == "counters") {
     h->counters = atoi(value) ? 1 : 0;
     h->inited = false;
@@ -402,6 +430,12 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(h->loop_threshold);
   else if (k == "counters")
     v = std::to_string(h->counters);
+  else if (k == "sched")
+    v = h->sched ? "sorted" : "lane";
+  else if (k == "track_steps")
+    v = std::to_string(h->track_steps);
+  else if (k == "track_min_lanes")
+    v = std::to_string(h->track_min_lanes);
   else if (k == "kernel")
     v = h->kernel_name;
   else
@@ -446,6 +480,7 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   const int bt = 256;
   if (h->layout == LAYOUT_CELL8) {
     size_t ncell = (size_t)(m.dnx + 1) * (m.dny + 1) * (m.dnz + 1);
+    if (ncell >= (1ull << 32)) return fail(h, "cvr_set_scene: density grid too large for 32-bit cell indices");
     CVR_CUDA(h, cudaMalloc(&h->d_dcells, ncell * 8 * sizeof(float)));
     int g = (int)std::min<size_t>((ncell + bt - 1) / bt, (size_t)h->sm_count * 32);
     k_build_density_cells<<<g, bt, 0, h->stream>>>(h->d_density, m.dnx, m.dny, m.dnz, (float4*)h->d_dcells);

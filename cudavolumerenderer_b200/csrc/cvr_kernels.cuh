@@ -53,6 +53,8 @@ struct KernelParams {
   int pullback;         // naive/streaming: o -= d*EPSILON at scatter (Q8)
   int rr;               // Russian roulette enabled (Defines.h:44)
   int rr_after_escape;  // thread-rng regeneration/streaming: the roulette draw is consumed after an escape (Q8)
+  int track_steps;      // sorted scheduler: Woodcock steps per round
+  int track_min_lanes;  // sorted scheduler: leave the step loop when fewer lanes are still tracking
 };
 
 enum : int { S_IDLE = 0, S_ISECT = 1, S_TRACK = 2, S_SCATTER = 3, S_BOUNDARY = 4, S_DONE = 5 };
@@ -72,11 +74,6 @@ CVR_DEV int code_from_normal(V3 n) {
   return 5;
 }
 
-template <int LAYOUT>
-CVR_DEV float density_lookup(const MediumParams& m, V3 p) {
-  if (LAYOUT == LAYOUT_CELL8) return density_cell8(m, p);
-  return density_linear(m, p);
-}
 template <int LAYOUT>
 CVR_DEV V3 albedo_lookup(const MediumParams& m, V3 p) {
   if (m.albedo_const) return v3(m.albedo_r, m.albedo_g, m.albedo_b);
@@ -100,205 +97,433 @@ struct RngSel<RNG_PHILOX> {
 #define CVR_MIN_BLOCKS 4
 #endif
 
+// Per-path registers.  One lane owns one path at a time.
+template <class Rng>
+struct PathRegs {
+  V3 o, d;
+  float thr_x, thr_y, thr_z;
+  float t, dist;
+  Rng rng;
+  uint32_t out_idx;
+  uint32_t path_lo;  // index of the path inside this launch (per-path debug output)
+  uint32_t bounces;
+  int ncode;
+  int state;
+};
+
+struct LaneCounters {
+  uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0;
+};
+
+// Loop invariants of the Woodcock step, hoisted once per thread (same values the
+// reference recomputes every iteration: Utilities.cuh:143, 129-132; Volume.h:40-45).
+struct TrackInv {
+  float inv_max_sigmat;  // 1 / (scale * max_density)
+  V3 q;                  // box_min / (box_max - box_min)
+  float rx, ry, rz;      // (float)(uint)(res - 1)
+  uint32_t nx, ny, nz;   // density dims
+  uint32_t sy, sz;       // cell strides (cell8) in cells
+};
+CVR_DEV TrackInv make_track_inv(const MediumParams& m) {
+  TrackInv I;
+  I.inv_max_sigmat = 1.0f / (m.scale * m.max_density);
+  I.q = m.box_min / (m.box_max - m.box_min);
+  I.rx = (float)(uint32_t)(m.dnx - 1), I.ry = (float)(uint32_t)(m.dny - 1), I.rz = (float)(uint32_t)(m.dnz - 1);
+  I.nx = m.dnx, I.ny = m.dny, I.nz = m.dnz;
+  I.sy = m.dnx + 1, I.sz = (uint32_t)(m.dnx + 1) * (uint32_t)(m.dny + 1);
+  return I;
+}
+
+// density at normalised coordinate p (A7) with the invariants hoisted; same values,
+// same operation order as density_cell8 / density_linear in cvr_device.cuh
+template <int LAYOUT>
+CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
+  if (LAYOUT != LAYOUT_CELL8) return density_linear(m, p);
+  float cx = p.x * I.rx, cy = p.y * I.ry, cz = p.z * I.rz;
+  int x1 = floorf(cx), y1 = floorf(cy), z1 = floorf(cz);
+  float fx = cx - x1, fy = cy - y1, fz = cz - z1;
+  uint32_t kx = min((uint32_t)(x1 + 1), I.nx), ky = min((uint32_t)(y1 + 1), I.ny),
+           kz = min((uint32_t)(z1 + 1), I.nz);
+  // cells < 2^32 is guaranteed by cvr_set_scene
+  uint32_t cell = kx + I.sy * ky + I.sz * kz;
+  float v[8];
+  ldg256(m.dcells + 8 * (size_t)cell, v);
+  return trilerp<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], fx, fy, fz);
+}
+
+// ---- regeneration: camera ray for launch-global work item g (A1/A2 prologue) ----
+template <int RNGM, class Rng>
+CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned long long per_tile,
+                        PathRegs<Rng>& R) {
+  uint32_t j = 0;
+  unsigned long long l = g;
+  if (P.n_launch_tiles > 1) {
+    j = (uint32_t)(g / per_tile);
+    l = g - (unsigned long long)j * per_tile;
+  }
+  unsigned long long path_id = P.path_begin + l;
+  uint32_t k = P.tile_first + j * P.tile_stride;
+  uint32_t off_x = P.off_x, off_y = P.off_y;
+  if (P.tile_origins) {
+    uint2 og = P.tile_origins[k];
+    off_x = og.x, off_y = og.y;
+  }
+  uint32_t seed_k = P.seed + k * P.seed_step;
+  if (RNGM == RNG_XORWOW_PATH) R.rng.init((int32_t)(seed_k + (uint32_t)path_id));
+  if (RNGM == RNG_PHILOX) R.rng.init((unsigned long long)seed_k + path_id);
+  uint32_t image_id = (uint32_t)(path_id % P.npix);
+  float u0 = R.rng.next();
+  float u1 = R.rng.next();
+  camera_ray(P.cam, image_id, off_x, off_y, u0, u1, R.o, R.d);
+  R.thr_x = R.thr_y = R.thr_z = 1.f;
+  R.bounces = 0;
+  R.path_lo = (uint32_t)g;
+  if (P.out_full) {
+    uint32_t px = image_id % P.tile_w, py = image_id / P.tile_w;
+    R.out_idx = (py + off_y) * P.out_stride + (px + off_x);
+  } else {
+    R.out_idx = image_id;
+  }
+  R.state = S_ISECT;
+}
+
+// ---- intersect (A5) + escape accumulation (A13) ----
+template <bool COUNT, class Rng>
+CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
+  if (COUNT) ++C.bounces;
+  V3 normal = v3(0, 0, 0);
+  bool inside;
+  if (!box_intersect(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside)) {
+    // escaped: throughput * Le, Le == 1 (Medium.h:174-177)
+    float rx = R.thr_x * 1.f, ry = R.thr_y * 1.f, rz = R.thr_z * 1.f;
+    if (P.per_path) P.per_path[R.path_lo] = make_float4(rx, ry, rz, 1.f);
+    if (P.out) {
+      float4* px = P.out + R.out_idx;
+      atomicAdd(&px->x, rx);
+      atomicAdd(&px->y, ry);
+      atomicAdd(&px->z, rz);
+      px->w = 1.f;
+    }
+    if (COUNT) ++C.esc;
+    if (P.rr_after_escape && P.rr) (void)R.rng.next();
+    R.state = S_IDLE;
+  } else if (!inside) {
+    R.ncode = code_from_normal(normal);
+    R.state = S_BOUNDARY;
+  } else {
+    R.ncode = code_from_normal(normal);
+    R.t = 0.f;
+    R.state = S_TRACK;
+  }
+}
+
+// ---- one Woodcock step (A6, A7): Utilities.cuh:146-152 ----
+template <int LAYOUT, bool COUNT, class Rng>
+CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C) {
+  float u = R.rng.next();
+  R.t += -logf(fmaxf(u, CVR_EPS)) * I.inv_max_sigmat;
+  V3 coord = (R.o + (R.t * R.d)) - I.q;
+  float event_density = P.med.scale * density_at<LAYOUT>(P.med, I, coord);
+  if (COUNT) ++C.dens;
+  bool go_on = (R.t <= R.dist);
+  if (go_on) go_on = (event_density * I.inv_max_sigmat < R.rng.next());
+  if (!go_on) R.state = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
+}
+
+// ---- Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) + bounce cap ----
+template <class Rng>
+CVR_DEV void do_roulette(const KernelParams& P, PathRegs<Rng>& R) {
+  R.state = S_ISECT;
+  if (P.rr) {
+    float p_survive = fminf(1.f, fmaxf(fmaxf(R.thr_x, R.thr_y), R.thr_z));
+    if (R.rng.next() > p_survive) R.state = S_IDLE;
+    R.thr_x = R.thr_x * 1.f / p_survive;
+    R.thr_y = R.thr_y * 1.f / p_survive;
+    R.thr_z = R.thr_z * 1.f / p_survive;
+  }
+  ++R.bounces;
+  if (P.max_bounces && R.bounces >= P.max_bounces) R.state = S_IDLE;
+}
+
+// ---- scatter event (A8, A9): NaiveVolPTsk_kernel.cuh:67-71 / Regeneration...:212-216 ----
+template <int LAYOUT, bool COUNT, class Rng>
+CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
+  if (P.pullback)
+    R.o = R.o + R.d * R.t - R.d * CVR_EPS;
+  else
+    R.o = R.o + R.d * R.t;
+  V3 ac = (R.o - P.med.box_min) / (P.med.box_max - P.med.box_min);
+  V3 albedo = albedo_lookup<LAYOUT>(P.med, ac);
+  if (COUNT) ++C.alb;
+  R.thr_x = R.thr_x * albedo.x, R.thr_y = R.thr_y * albedo.y, R.thr_z = R.thr_z * albedo.z;
+  float e1 = R.rng.next();
+  float e2 = R.rng.next();
+  R.d = hg_sample(R.d, P.med.hg_g, e1, e2);
+  do_roulette(P, R);
+}
+
+// ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
+template <class Rng>
+CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
+  Frame frame;
+  frame.from_z(normal_from_code(R.ncode));
+  V3 dir = frame.to_local(normalize(v3(-R.d.x, -R.d.y, -R.d.z)));
+  R.o = R.o + R.d * R.dist;
+  float weight = 1;
+  // the sampler writes the LOCAL direction into the ray even when it then fails
+  if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, R.rng, R.d, weight)) {
+    R.thr_x *= weight, R.thr_y *= weight, R.thr_z *= weight;
+    R.d = frame.to_world(R.d);
+    R.o = R.o + R.d * CVR_EPS;
+  }
+  do_roulette(P, R);
+}
+
+template <bool COUNT>
+CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lane) {
+  if (!COUNT) return;
+  const unsigned FULL = 0xffffffffu;
+  for (int s = 16; s > 0; s >>= 1) {
+    C.paths += __shfl_xor_sync(FULL, C.paths, s);
+    C.bounces += __shfl_xor_sync(FULL, C.bounces, s);
+    C.dens += __shfl_xor_sync(FULL, C.dens, s);
+    C.alb += __shfl_xor_sync(FULL, C.alb, s);
+    C.esc += __shfl_xor_sync(FULL, C.esc, s);
+  }
+  if (lane == 0) {  // one atomic per warp per counter
+    atomicAdd(&P.ctr->paths, (unsigned long long)C.paths);
+    atomicAdd(&P.ctr->bounces, (unsigned long long)C.bounces);
+    atomicAdd(&P.ctr->density_lookups, (unsigned long long)C.dens);
+    atomicAdd(&P.ctr->albedo_lookups, (unsigned long long)C.alb);
+    atomicAdd(&P.ctr->escaped, (unsigned long long)C.esc);
+  }
+}
+
+// claim path ids for the idle lanes of this warp with one 64-bit atomic
+template <int RNGM, bool COUNT, class Rng>
+CVR_DEV void warp_regenerate(const KernelParams& P, unsigned idle_mask, unsigned lane, unsigned long long total,
+                             unsigned long long per_tile, bool& exhausted, PathRegs<Rng>& R, LaneCounters& C) {
+  const unsigned FULL = 0xffffffffu;
+  if (!exhausted) {
+    int n = __popc(idle_mask);
+    int leader = __ffs(idle_mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(P.head, (unsigned long long)n);
+    base = __shfl_sync(FULL, base, leader);
+    if (R.state == S_IDLE) {
+      unsigned long long g = base + __popc(idle_mask & ((1u << lane) - 1u));
+      if (g < total) {
+        start_path<RNGM>(P, g, per_tile, R);
+        if (COUNT) ++C.paths;
+      } else {
+        R.state = S_DONE;
+      }
+    }
+    exhausted = (base + (unsigned long long)n >= total);
+  } else if (R.state == S_IDLE) {
+    R.state = S_DONE;
+  }
+}
+
+// =============================================================================
+// Scheduler 1: lane-persistent ("while-while"): a lane keeps its path in registers;
+// the warp alternates between the Woodcock loop and the event phase.
+// =============================================================================
 template <int RNGM, int LAYOUT, bool COUNT>
 __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     k_volpt(const __grid_constant__ KernelParams P) {
   typedef typename RngSel<RNGM>::type Rng;
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lane_lt = (1u << lane) - 1u;
 
-  Rng rng;
+  PathRegs<Rng> R;
+  R.o = v3(0, 0, 0), R.d = v3(0, 0, 1);
+  R.thr_x = R.thr_y = R.thr_z = 1.f;
+  R.t = R.dist = 0.f;
+  R.out_idx = R.path_lo = R.bounces = 0;
+  R.ncode = 0;
+  R.state = S_IDLE;
   if (RNGM == RNG_XORWOW_THREAD) {
     // RegenerationVolPTsk_kernel.cuh:151,156: Rng rng(seed + tid), once per thread
     uint32_t tid = threadIdx.x + blockDim.x * blockIdx.x;
-    rng.init((int32_t)(P.seed + tid));
+    R.rng.init((int32_t)(P.seed + tid));
   }
-
+  LaneCounters C;
   const unsigned long long per_tile = P.path_end - P.path_begin;
   const unsigned long long total = per_tile * P.n_launch_tiles;
-
-  // loop invariants of Woodcock tracking (Utilities.cuh:143, 129-132)
-  const float inv_max_sigmat = 1.0f / (P.med.scale * P.med.max_density);
-  const V3 q = P.med.box_min / (P.med.box_max - P.med.box_min);
-
-  int state = S_IDLE;
+  const TrackInv I = make_track_inv(P.med);
   bool exhausted = false;
-  V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
-  float thr_x = 1.f, thr_y = 1.f, thr_z = 1.f;
-  float t = 0.f, dist = 0.f;
-  int ncode = 0;
-  uint32_t out_idx = 0, bounces = 0;
-  unsigned long long my_path = 0;
-  uint32_t c_paths = 0, c_bounces = 0, c_dens = 0, c_alb = 0, c_esc = 0;
 
   for (;;) {
-    // ------------------------------------------------------------ regeneration
-    unsigned idle = __ballot_sync(FULL, state == S_IDLE);
-    if (idle) {
-      if (!exhausted) {
-        int n = __popc(idle);
-        int leader = __ffs(idle) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(P.head, (unsigned long long)n);
-        base = __shfl_sync(FULL, base, leader);
-        if (state == S_IDLE) {
-          unsigned long long g = base + __popc(idle & lane_lt);
-          if (g < total) {
-            // which tile / path / stream
-            uint32_t j = 0;
-            unsigned long long l = g;
-            if (P.n_launch_tiles > 1) {
-              j = (uint32_t)(g / per_tile);
-              l = g - (unsigned long long)j * per_tile;
-            }
-            unsigned long long path_id = P.path_begin + l;
-            uint32_t k = P.tile_first + j * P.tile_stride;
-            uint32_t off_x = P.off_x, off_y = P.off_y;
-            if (P.tile_origins) {
-              uint2 og = P.tile_origins[k];
-              off_x = og.x, off_y = og.y;
-            }
-            uint32_t seed_k = P.seed + k * P.seed_step;
-            if (RNGM == RNG_XORWOW_PATH) rng.init((int32_t)(seed_k + (uint32_t)path_id));
-            if (RNGM == RNG_PHILOX) rng.init((unsigned long long)seed_k + path_id);
-            uint32_t image_id = (uint32_t)(path_id % P.npix);
-            float u0 = rng.next();
-            float u1 = rng.next();
-            camera_ray(P.cam, image_id, off_x, off_y, u0, u1, o, d);
-            thr_x = thr_y = thr_z = 1.f;
-            bounces = 0;
-            my_path = g;
-            if (P.out_full) {
-              uint32_t px = image_id % P.tile_w, py = image_id / P.tile_w;
-              out_idx = (py + off_y) * P.out_stride + (px + off_x);
-            } else {
-              out_idx = image_id;
-            }
-            if (COUNT) ++c_paths;
-            state = S_ISECT;
-          } else {
-            state = S_DONE;
-          }
-        }
-        exhausted = (base + (unsigned long long)n >= total);
-      } else if (state == S_IDLE) {
-        state = S_DONE;
-      }
-    }
-    if (__all_sync(FULL, state == S_DONE)) break;
+    unsigned idle = __ballot_sync(FULL, R.state == S_IDLE);
+    if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
+    if (__all_sync(FULL, R.state == S_DONE)) break;
 
-    // ------------------------------------------------------------ intersect (A5)
-    if (state == S_ISECT) {
-      if (COUNT) ++c_bounces;
-      V3 normal = v3(0, 0, 0);
-      bool inside;
-      if (!box_intersect(P.med.box_min, P.med.box_max, o, d, dist, normal, inside)) {
-        // escaped: throughput * Le, Le == 1 (Medium.h:174-177); A13
-        float rx = thr_x * 1.f, ry = thr_y * 1.f, rz = thr_z * 1.f;
-        if (P.per_path) P.per_path[my_path] = make_float4(rx, ry, rz, 1.f);
-        if (P.out) {
-          float4* px = P.out + out_idx;
-          atomicAdd(&px->x, rx);
-          atomicAdd(&px->y, ry);
-          atomicAdd(&px->z, rz);
-          px->w = 1.f;
-        }
-        if (COUNT) ++c_esc;
-        if (P.rr_after_escape && P.rr) (void)rng.next();
-        state = S_IDLE;
-      } else if (!inside) {
-        ncode = code_from_normal(normal);
-        state = S_BOUNDARY;
-      } else {
-        ncode = code_from_normal(normal);
-        t = 0.f;
-        state = S_TRACK;
-      }
-    }
+    if (R.state == S_ISECT) do_isect<COUNT>(P, R, C);
 
-    // ------------------------------------------------------------ Woodcock steps (A6, A7)
     {
-      const int n_parked = __popc(__ballot_sync(FULL, state == S_DONE));
+      const int n_parked = __popc(__ballot_sync(FULL, R.state == S_DONE));
       // at least one step per outer iteration, then yield to the event phase as soon
       // as `loop_threshold` lanes are waiting for it
       for (bool first = true;; first = false) {
-        unsigned trk = __ballot_sync(FULL, state == S_TRACK);
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
         if (trk == 0) break;
         int waiting = 32 - n_parked - __popc(trk);
         if (!first && waiting >= P.loop_threshold) break;
-        if (state == S_TRACK) {
-          float u = rng.next();
-          t += -logf(fmaxf(u, CVR_EPS)) * inv_max_sigmat;
-          V3 coord = (o + (t * d)) - q;
-          float event_density = P.med.scale * density_lookup<LAYOUT>(P.med, coord);
-          if (COUNT) ++c_dens;
-          bool go_on = (t <= dist);
-          if (go_on) go_on = (event_density * inv_max_sigmat < rng.next());
-          if (!go_on) state = (t < dist) ? S_SCATTER : S_BOUNDARY;
-        }
+        if (R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
       }
     }
 
-    // ------------------------------------------------------------ events
-    if (state == S_SCATTER || state == S_BOUNDARY) {
-      if (state == S_SCATTER) {
-        // NaiveVolPTsk_kernel.cuh:67-71 / RegenerationVolPTsk_kernel.cuh:212-216
-        if (P.pullback)
-          o = o + d * t - d * CVR_EPS;
-        else
-          o = o + d * t;
-        V3 ac = (o - P.med.box_min) / (P.med.box_max - P.med.box_min);
-        V3 albedo = albedo_lookup<LAYOUT>(P.med, ac);
-        if (COUNT) ++c_alb;
-        thr_x = thr_x * albedo.x, thr_y = thr_y * albedo.y, thr_z = thr_z * albedo.z;
-        float e1 = rng.next();
-        float e2 = rng.next();
-        d = hg_sample(d, P.med.hg_g, e1, e2);
-      } else {
-        // NaiveVolPTsk_kernel.cuh:50-65
-        Frame frame;
-        frame.from_z(normal_from_code(ncode));
-        V3 dir = frame.to_local(normalize(v3(-d.x, -d.y, -d.z)));
-        o = o + d * dist;
-        float weight = 1;
-        if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, d, weight)) {
-          thr_x *= weight, thr_y *= weight, thr_z *= weight;
-          d = frame.to_world(d);
-          o = o + d * CVR_EPS;
-        }
-      }
-      // Russian roulette (NaiveVolPTsk_kernel.cuh:75-84)
-      state = S_ISECT;
-      if (P.rr) {
-        float p_survive = fminf(1.f, fmaxf(fmaxf(thr_x, thr_y), thr_z));
-        if (rng.next() > p_survive) state = S_IDLE;
-        thr_x = thr_x * 1.f / p_survive;
-        thr_y = thr_y * 1.f / p_survive;
-        thr_z = thr_z * 1.f / p_survive;
-      }
-      ++bounces;
-      if (P.max_bounces && bounces >= P.max_bounces) state = S_IDLE;
-    }
+    if (R.state == S_SCATTER)
+      do_scatter<LAYOUT, COUNT>(P, R, C);
+    else if (R.state == S_BOUNDARY)
+      do_boundary(P, R);
   }
+  flush_counters<COUNT>(P, C, lane);
+}
 
-  if (COUNT) {
-    // one atomic per warp per counter
-    for (int s = 16; s > 0; s >>= 1) {
-      c_paths += __shfl_xor_sync(FULL, c_paths, s);
-      c_bounces += __shfl_xor_sync(FULL, c_bounces, s);
-      c_dens += __shfl_xor_sync(FULL, c_dens, s);
-      c_alb += __shfl_xor_sync(FULL, c_alb, s);
-      c_esc += __shfl_xor_sync(FULL, c_esc, s);
-    }
-    if (lane == 0) {
-      atomicAdd(&P.ctr->paths, (unsigned long long)c_paths);
-      atomicAdd(&P.ctr->bounces, (unsigned long long)c_bounces);
-      atomicAdd(&P.ctr->density_lookups, (unsigned long long)c_dens);
-      atomicAdd(&P.ctr->albedo_lookups, (unsigned long long)c_alb);
-      atomicAdd(&P.ctr->escaped, (unsigned long long)c_esc);
-    }
+// =============================================================================
+// Scheduler 2: block-sorted wavefront.  The CVR_BLOCK paths of a CTA live in shared
+// memory (80-byte slots).  Every round the slots are counting-sorted by state
+// (TRACK, SCATTER, BOUNDARY, IDLE, DONE) so that the 32 lanes of a warp pick up 32
+// paths in the SAME state, run that state's event (+ the following intersect), then
+// up to `track_steps` Woodcock steps, and store the paths back.  Each path's own
+// operation and RNG-draw order is unchanged; only which lane executes it changes.
+// =============================================================================
+struct __align__(16) PathSlot {
+  float4 q0;  // o.xyz, t
+  float4 q1;  // d.xyz, dist
+  float4 q2;  // thr.xyz, meta (state | ncode << 3 | bounces << 6) as bits
+  uint4 q3;   // rng v0..v3
+  uint4 q4;   // rng v4, d, out_idx, path_lo
+};
+
+CVR_DEV void slot_store(PathSlot& s, const PathRegs<Xorwow>& R) {
+  uint32_t meta = (uint32_t)R.state | ((uint32_t)R.ncode << 3) | (R.bounces << 6);
+  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.t);
+  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, R.dist);
+  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, __uint_as_float(meta));
+  s.q3 = make_uint4(R.rng.v0, R.rng.v1, R.rng.v2, R.rng.v3);
+  s.q4 = make_uint4(R.rng.v4, R.rng.d, R.out_idx, R.path_lo);
+}
+CVR_DEV void slot_load(const PathSlot& s, PathRegs<Xorwow>& R) {
+  float4 a = s.q0, b = s.q1, c = s.q2;
+  uint4 e = s.q3, f = s.q4;
+  R.o = v3(a.x, a.y, a.z), R.t = a.w;
+  R.d = v3(b.x, b.y, b.z), R.dist = b.w;
+  R.thr_x = c.x, R.thr_y = c.y, R.thr_z = c.z;
+  uint32_t meta = __float_as_uint(c.w);
+  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
+  R.rng.v0 = e.x, R.rng.v1 = e.y, R.rng.v2 = e.z, R.rng.v3 = e.w;
+  R.rng.v4 = f.x, R.rng.d = f.y, R.out_idx = f.z, R.path_lo = f.w;
+}
+
+CVR_DEV int sort_key(int state) {
+  // TRACK 0, SCATTER 1, BOUNDARY 2, IDLE 3, DONE 4
+  return state == S_TRACK ? 0 : state == S_SCATTER ? 1 : state == S_BOUNDARY ? 2 : state == S_IDLE ? 3 : 4;
+}
+
+template <int RNGM, int LAYOUT, bool COUNT>
+__global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
+    k_volpt_sorted(const __grid_constant__ KernelParams P) {
+  typedef Xorwow Rng;
+  constexpr int NW = CVR_BLOCK / 32;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+
+  __shared__ PathSlot s_slot[CVR_BLOCK];
+  __shared__ uint16_t s_list[CVR_BLOCK];
+  __shared__ uint8_t s_state[CVR_BLOCK];
+  __shared__ uint32_t s_cnt[5 * NW];  // per (key, warp) counts -> exclusive offsets
+  __shared__ int s_exhausted;
+
+  LaneCounters C;
+  const unsigned long long per_tile = P.path_end - P.path_begin;
+  const unsigned long long total = per_tile * P.n_launch_tiles;
+  const TrackInv I = make_track_inv(P.med);
+
+  {  // all slots start idle
+    PathRegs<Rng> R;
+    R.o = v3(0, 0, 0), R.d = v3(0, 0, 1);
+    R.thr_x = R.thr_y = R.thr_z = 1.f;
+    R.t = R.dist = 0.f;
+    R.out_idx = R.path_lo = R.bounces = 0;
+    R.ncode = 0;
+    R.state = S_IDLE;
+    R.rng.init((int32_t)(P.seed + threadIdx.x + blockDim.x * blockIdx.x));  // per-slot stream (thread-rng mode)
+    slot_store(s_slot[threadIdx.x], R);
+    s_state[threadIdx.x] = S_IDLE;
+    if (threadIdx.x == 0) s_exhausted = 0;
   }
+  __syncthreads();
+
+  for (;;) {
+    // ---------------------------------------------------------------- sort slots by state
+    const int my_key = sort_key(s_state[threadIdx.x]);
+    uint32_t my_rank = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      unsigned m = __ballot_sync(FULL, my_key == k);
+      if (my_key == k) my_rank = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_cnt[k * NW + warp] = __popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive scan over the 5*NW counters in key-major order
+      uint32_t a = lane < 5 * NW ? s_cnt[lane] : 0u;
+      uint32_t b = (lane + 32) < 5 * NW ? s_cnt[lane + 32] : 0u;
+      uint32_t ia = a, ib = b;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        uint32_t ta = __shfl_up_sync(FULL, ia, s), tb = __shfl_up_sync(FULL, ib, s);
+        if ((int)lane >= s) ia += ta, ib += tb;
+      }
+      uint32_t tot_a = __shfl_sync(FULL, ia, 31);
+      if (lane < 5 * NW) s_cnt[lane] = ia - a;
+      if ((lane + 32) < 5 * NW) s_cnt[lane + 32] = tot_a + ib - b;
+    }
+    __syncthreads();
+    s_list[s_cnt[my_key * NW + warp] + my_rank] = (uint16_t)threadIdx.x;
+    // first index of the DONE group = number of live slots
+    const uint32_t n_live = s_cnt[4 * NW];
+    const uint32_t n_track = s_cnt[1 * NW];  // first index of the SCATTER group
+    __syncthreads();
+    if (n_live == 0) break;
+
+    // ---------------------------------------------------------------- one round on my slot
+    const unsigned slot = s_list[threadIdx.x];
+    PathRegs<Rng> R;
+    slot_load(s_slot[slot], R);
+    bool exhausted = s_exhausted != 0;
+
+    if (__any_sync(FULL, R.state != S_DONE)) {
+      unsigned idle = __ballot_sync(FULL, R.state == S_IDLE);
+      if (idle) {
+        bool was = exhausted;
+        warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
+        if (exhausted && !was && lane == 0) s_exhausted = 1;
+      }
+      if (R.state == S_SCATTER)
+        do_scatter<LAYOUT, COUNT>(P, R, C);
+      else if (R.state == S_BOUNDARY)
+        do_boundary(P, R);
+      if (R.state == S_ISECT) do_isect<COUNT>(P, R, C);
+      // Woodcock steps; stop early when few lanes remain unless the CTA is draining
+      const bool draining = n_track < 64u;
+      for (int it = 0; it < P.track_steps; ++it) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+        if (trk == 0) break;
+        if (it > 0 && !draining && __popc(trk) < P.track_min_lanes) break;
+        if (R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
+      }
+      // states ISECT cannot persist across rounds
+      slot_store(s_slot[slot], R);
+      s_state[slot] = (uint8_t)R.state;
+    }
+    __syncthreads();
+  }
+  flush_counters<COUNT>(P, C, lane);
 }
 
 // ---------------------------------------------------------------- layout builders
@@ -384,7 +609,7 @@ __global__ void k_debug_lookup(MediumParams m, const float* p, int n, float* den
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V3 c = v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
-  dens[i] = density_lookup<LAYOUT>(m, c);
+  dens[i] = density_at<LAYOUT>(m, make_track_inv(m), c);
   V3 a = albedo_lookup<LAYOUT>(m, c);
   alb[3 * i] = a.x, alb[3 * i + 1] = a.y, alb[3 * i + 2] = a.z;
 }

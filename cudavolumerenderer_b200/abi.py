@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcvr_b200.so")
+LIB_PATH = os.environ.get("CVR_B200_LIB", os.path.join(HERE, "libcvr_b200.so"))  # override: kernel-tuning experiments only
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)

@@ -134,6 +134,14 @@ kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count) {
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
 #undef CVR_K
+#define CVR_K(R, L)                                      \
+  if (sched == 2 && rng_mode == R && layout == L)        \
+    return count ? (kernel_fn)k_volpt_queued<R, L, true> : (kernel_fn)k_volpt_queued<R, L, false>;
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
+#undef CVR_K
   return nullptr;
 }
 
@@ -388,8 +396,10 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
       h->sched = 0;
     else if (v == "sorted")
       h->sched = 1;
+    else if (v == "queued")
+      h->sched = 2;
     else
-      return fail(h, "sched: unknown value '%s' (lane | sorted)", value);
+      return fail(h, "sched: unknown value '%s' (lane | sorted | queued)", value);
     h->inited = false;
   } else if (k == "track_steps") {
     int t = atoi(value);
@@ -431,7 +441,7 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "counters")
     v = std::to_string(h->counters);
   else if (k == "sched")
-    v = h->sched ? "sorted" : "lane";
+    v = h->sched == 2 ? "queued" : h->sched ? "sorted" : "lane";
   else if (k == "track_steps")
     v = std::to_string(h->track_steps);
   else if (k == "track_min_lanes")

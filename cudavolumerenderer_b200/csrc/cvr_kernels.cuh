@@ -526,6 +526,172 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   flush_counters<COUNT>(P, C, lane);
 }
 
+// =============================================================================
+// Scheduler 3: decoupled state queues ("queued wavefront").  A CTA owns
+// CVR_QSLOTS path slots in shared memory and one ring-buffer queue of slot ids per
+// state (TRACK, SCATTER, BOUNDARY, IDLE).  There are NO block barriers in the steady
+// state: every warp repeatedly pops up to 32 slot ids from the fullest queue, so its 32
+// lanes hold paths in the SAME state, runs that state's event (+ the following
+// intersect) and Woodcock steps while enough lanes stay busy, writes the paths back
+// and pushes every slot onto the queue of its new state (warp-aggregated
+// reserve -> write -> ordered commit).  Per-path operation and RNG order unchanged.
+// =============================================================================
+#ifndef CVR_QSLOTS
+#define CVR_QSLOTS 512
+#endif
+
+struct QueueCtl {
+  unsigned int head[4];  // pop cursor
+  unsigned int tail[4];  // committed push cursor
+  unsigned int resv[4];  // reserved push cursor
+  unsigned int n_done;
+  int exhausted;
+};
+
+CVR_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+
+template <int RNGM, int LAYOUT, bool COUNT>
+__global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
+    k_volpt_queued(const __grid_constant__ KernelParams P) {
+  typedef Xorwow Rng;
+  constexpr unsigned N = CVR_QSLOTS;
+  static_assert((N & (N - 1)) == 0, "CVR_QSLOTS must be a power of two");
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lane_lt = (1u << lane) - 1u;
+
+  __shared__ PathSlot s_slot[N];
+  __shared__ uint16_t s_q[4][N];
+  __shared__ QueueCtl s_ctl;
+
+  LaneCounters C;
+  const unsigned long long per_tile = P.path_end - P.path_begin;
+  const unsigned long long total = per_tile * P.n_launch_tiles;
+  const TrackInv I = make_track_inv(P.med);
+
+  // all slots start idle, queued on the IDLE queue (key 3)
+  for (unsigned i = threadIdx.x; i < N; i += blockDim.x) {
+    PathRegs<Rng> R;
+    R.o = v3(0, 0, 0), R.d = v3(0, 0, 1);
+    R.thr_x = R.thr_y = R.thr_z = 1.f;
+    R.t = R.dist = 0.f;
+    R.out_idx = R.path_lo = R.bounces = 0;
+    R.ncode = 0;
+    R.state = S_IDLE;
+    R.rng.init((int32_t)(P.seed + i + N * blockIdx.x));  // per-slot stream (thread-rng mode)
+    slot_store(s_slot[i], R);
+    s_q[3][i] = (uint16_t)i;
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) s_ctl.head[k] = s_ctl.tail[k] = s_ctl.resv[k] = 0u;
+    s_ctl.tail[3] = s_ctl.resv[3] = N;
+    s_ctl.n_done = 0u;
+    s_ctl.exhausted = 0;
+  }
+  __syncthreads();
+
+  for (;;) {
+    // ---------------------------------------------------------------- pop a batch
+    // lane 0 picks the fullest queue; the lanes READ their candidate entries first and
+    // only then lane 0 claims them with a CAS on the pop cursor.  Entries in
+    // [head, tail) are live and cannot be overwritten (a queue never holds more than N
+    // slots), so a successful CAS proves the ids read were the ones claimed.  (Claiming
+    // first and reading afterwards would let a fast warp wrap the ring over them.)
+    int key = -1;
+    unsigned h = 0, n = 0;
+    if (lane == 0) {
+      unsigned best = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned hk = ld_volatile_u32(&s_ctl.head[k]);
+        unsigned c = ld_volatile_u32(&s_ctl.tail[k]) - hk;
+        if ((int)c > (int)best) best = c, key = k, h = hk;
+      }
+      n = best < 32u ? best : 32u;
+    }
+    key = __shfl_sync(FULL, key, 0);
+    if (key < 0) {
+      unsigned nd = lane == 0 ? ld_volatile_u32(&s_ctl.n_done) : 0u;
+      if (__shfl_sync(FULL, nd, 0) >= N) break;
+      __nanosleep(100);
+      continue;
+    }
+    h = __shfl_sync(FULL, h, 0);
+    n = __shfl_sync(FULL, n, 0);
+    __threadfence_block();
+    const bool mine = lane < n;
+    unsigned slot = 0;
+    if (mine) slot = *(volatile uint16_t*)&s_q[key][(h + lane) & (N - 1)];
+    int ok = 0;
+    if (lane == 0) ok = atomicCAS(&s_ctl.head[key], h, h + n) == h;
+    if (!__shfl_sync(FULL, ok, 0)) continue;  // somebody else popped first: start over
+    __threadfence_block();
+
+    PathRegs<Rng> R;
+    R.state = S_DONE;
+    if (mine) slot_load(s_slot[slot], R);
+
+    // ---------------------------------------------------------------- event of this batch
+    if (key == 3) {
+      unsigned idle = __ballot_sync(FULL, mine && R.state == S_IDLE);
+      bool exhausted = ld_volatile_u32((const unsigned int*)&s_ctl.exhausted) != 0u;
+      bool was = exhausted;
+      if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
+      if (exhausted && !was && lane == 0) s_ctl.exhausted = 1;
+    } else if (key == 1) {
+      if (mine) do_scatter<LAYOUT, COUNT>(P, R, C);
+    } else if (key == 2) {
+      if (mine) do_boundary(P, R);
+    }
+    if (R.state == S_ISECT) do_isect<COUNT>(P, R, C);
+
+    // ---------------------------------------------------------------- Woodcock steps
+    for (int it = 0; it < P.track_steps; ++it) {
+      unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+      if (trk == 0) break;
+      if (it > 0 && __popc(trk) < P.track_min_lanes) {
+        // few lanes left: requeue them so they merge into a full batch -- unless
+        // nobody else is queued for tracking
+        unsigned waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
+        if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+      }
+      if (R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
+    }
+
+    // ---------------------------------------------------------------- write back + push
+    if (mine) slot_store(s_slot[slot], R);
+    const int nk = mine ? sort_key(R.state) : 5;
+    unsigned my_p = 0, commit_mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned m = __ballot_sync(FULL, nk == k);
+      if (m) {
+        int leader = __ffs(m) - 1;
+        unsigned p = 0;
+        if ((int)lane == leader) p = atomicAdd(&s_ctl.resv[k], (unsigned)__popc(m));
+        p = __shfl_sync(FULL, p, leader);
+        if (nk == k) s_q[k][(p + __popc(m & lane_lt)) & (N - 1)] = (uint16_t)slot;
+        if ((int)lane == leader) my_p = p, commit_mask = m;
+      }
+    }
+    unsigned done_m = __ballot_sync(FULL, nk == 4);
+    // every lane's slot + queue stores must be visible before ANY leader publishes them:
+    // fence my own stores, then order the warp (lanes do not run in lock step)
+    __threadfence_block();
+    __syncwarp();
+    if (commit_mask) {
+      // ordered commit: our entries become poppable after every earlier reservation
+      const int k = nk;
+      const unsigned cnt = (unsigned)__popc(commit_mask);
+      while (atomicCAS(&s_ctl.tail[k], my_p, my_p + cnt) != my_p) {
+      }
+    }
+    if (done_m && lane == 0) atomicAdd(&s_ctl.n_done, (unsigned)__popc(done_m));
+    __syncwarp();
+  }
+  flush_counters<COUNT>(P, C, lane);
+}
+
 // ---------------------------------------------------------------- layout builders
 // cell (kx,ky,kz) <- the 8 values the reference's 8 texture fetches return for
 // x1 = kx-1 (see cell_index in cvr_device.cuh).

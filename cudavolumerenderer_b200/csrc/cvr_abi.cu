@@ -48,8 +48,8 @@ struct cvr_renderer {
   int blocks_per_sm = 0;  // 0 = occupancy query
   int loop_threshold = 16;
   int counters = 1;
-  int sched = 1;  // 0 = lane-persistent, 1 = block-sorted wavefront
-  int track_steps = 4;
+  int sched = 2;  // 0 = lane-persistent, 1 = block-sorted wavefront, 2 = queued wavefront
+  int track_steps = 8;
   int track_min_lanes = 8;
 
   // launcher state
@@ -198,6 +198,19 @@ void collect_timing(cvr_handle h) {
   h->timing.clear();
 }
 
+// Woodcock-loop invariants, same fp32 operations the kernels used to perform per thread
+void fill_track_inv(KernelParams& P) {
+  const MediumParams& m = P.med;
+  TrackInv& I = P.inv;
+  volatile float prod = m.scale * m.max_density;  // keep the two roundings separate
+  I.inv_max_sigmat = 1.0f / prod;
+  volatile float ex = m.box_max.x - m.box_min.x, ey = m.box_max.y - m.box_min.y, ez = m.box_max.z - m.box_min.z;
+  I.qx = m.box_min.x / ex, I.qy = m.box_min.y / ey, I.qz = m.box_min.z / ez;
+  I.rx = (float)(uint32_t)(m.dnx - 1), I.ry = (float)(uint32_t)(m.dny - 1), I.rz = (float)(uint32_t)(m.dnz - 1);
+  I.nx = m.dnx, I.ny = m.dny, I.nz = m.dnz;
+  I.sy = m.dnx + 1, I.sz = (uint32_t)(m.dnx + 1) * (uint32_t)(m.dny + 1);
+}
+
 // fills the per-launch part of the kernel parameters and launches
 int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const uint2* origins,
            uint32_t n_launch_tiles, uint32_t tile_first, uint32_t tile_stride, uint32_t seed,
@@ -208,6 +221,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   if (set_device(h)) return 1;
   if (ensure_allocated(h) || ensure_init(h)) return 1;
   KernelParams& P = h->P;
+  fill_track_inv(P);
   P.npix = (uint32_t)(P.cam.res_x * P.cam.res_y);  // (uint)(c_resolution.x * c_resolution.y)
   P.tile_w = (uint32_t)P.cam.res_x;
   P.path_begin = path_begin;
@@ -357,7 +371,7 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
       h->rng_mode = RNG_PHILOX;
     else
       return fail(h, "rng: unknown value '%s'", value);
-    if (h->rng_mode == RNG_PHILOX) h->sched = 0;  // the sorted scheduler stores XORWOW state only
+    if (h->rng_mode == RNG_PHILOX) h->sched = 0;  // the wavefront schedulers store XORWOW state only
     if (h->variant == VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD)
       return fail(h, "rng=xorwow-thread is not a naiveSK mode (NaiveVolPTsk_kernel.cuh:22 seeds per path)");
     h->inited = false;
@@ -868,15 +882,16 @@ int cvr_debug_lookup(cvr_handle h, const float* p, int n, float* dens, float* al
   if (!h->scene_set) return fail(h, "cvr_debug_lookup before cvr_set_scene");
   if (!p || n <= 0 || !dens || !alb) return fail(h, "cvr_debug_lookup: bad arguments");
   if (set_device(h)) return 1;
+  fill_track_inv(h->P);
   float *d_p, *d_d, *d_a;
   CVR_CUDA(h, cudaMalloc(&d_p, (size_t)n * 12));
   CVR_CUDA(h, cudaMalloc(&d_d, (size_t)n * 4));
   CVR_CUDA(h, cudaMalloc(&d_a, (size_t)n * 12));
   CVR_CUDA(h, cudaMemcpyAsync(d_p, p, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
   if (h->layout == LAYOUT_CELL8)
-    k_debug_lookup<LAYOUT_CELL8><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, d_p, n, d_d, d_a);
+    k_debug_lookup<LAYOUT_CELL8><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, h->P.inv, d_p, n, d_d, d_a);
   else
-    k_debug_lookup<LAYOUT_LINEAR><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, d_p, n, d_d, d_a);
+    k_debug_lookup<LAYOUT_LINEAR><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, h->P.inv, d_p, n, d_d, d_a);
   CVR_CUDA(h, cudaGetLastError());
   CVR_CUDA(h, cudaMemcpyAsync(dens, d_d, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   CVR_CUDA(h, cudaMemcpyAsync(alb, d_a, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));

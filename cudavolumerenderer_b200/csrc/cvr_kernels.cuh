@@ -27,9 +27,18 @@ struct DeviceCounters {
   unsigned long long paths, bounces, density_lookups, albedo_lookups, escaped, speculative;
 };
 
+struct TrackInv {
+  float inv_max_sigmat;  // 1 / (scale * max_density)
+  float qx, qy, qz;      // box_min / (box_max - box_min)
+  float rx, ry, rz;      // (float)(uint)(res - 1)
+  uint32_t nx, ny, nz;   // density dims
+  uint32_t sy, sz;       // cell strides (cell8) in cells
+};
+
 struct KernelParams {
   CameraParams cam;
   MediumParams med;
+  TrackInv inv;
   // work: this launch runs, for each of n_launch_tiles tiles, the path ids
   // [path_begin, path_end) of that tile (path id = sample * npix + pixel).
   unsigned long long path_begin, path_end;
@@ -115,25 +124,10 @@ struct LaneCounters {
   uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0;
 };
 
-// Loop invariants of the Woodcock step, hoisted once per thread (same values the
-// reference recomputes every iteration: Utilities.cuh:143, 129-132; Volume.h:40-45).
-struct TrackInv {
-  float inv_max_sigmat;  // 1 / (scale * max_density)
-  V3 q;                  // box_min / (box_max - box_min)
-  float rx, ry, rz;      // (float)(uint)(res - 1)
-  uint32_t nx, ny, nz;   // density dims
-  uint32_t sy, sz;       // cell strides (cell8) in cells
-};
-CVR_DEV TrackInv make_track_inv(const MediumParams& m) {
-  TrackInv I;
-  I.inv_max_sigmat = 1.0f / (m.scale * m.max_density);
-  I.q = m.box_min / (m.box_max - m.box_min);
-  I.rx = (float)(uint32_t)(m.dnx - 1), I.ry = (float)(uint32_t)(m.dny - 1), I.rz = (float)(uint32_t)(m.dnz - 1);
-  I.nx = m.dnx, I.ny = m.dny, I.nz = m.dnz;
-  I.sy = m.dnx + 1, I.sz = (uint32_t)(m.dnx + 1) * (uint32_t)(m.dny + 1);
-  return I;
-}
-
+// Loop invariants of the Woodcock step (the reference recomputes them every
+// iteration: Utilities.cuh:143, 129-132; Volume.h:40-45).  They are computed ONCE on
+// the host with the same fp32 operations (cvr_abi.cu: fill_track_inv) and live in the
+// kernel-parameter constant bank, so they cost neither registers nor instructions.
 // density at normalised coordinate p (A7) with the invariants hoisted; same values,
 // same operation order as density_cell8 / density_linear in cvr_device.cuh
 template <int LAYOUT>
@@ -222,7 +216,7 @@ template <int LAYOUT, bool COUNT, class Rng>
 CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C) {
   float u = R.rng.next();
   R.t += -logf(fmaxf(u, CVR_EPS)) * I.inv_max_sigmat;
-  V3 coord = (R.o + (R.t * R.d)) - I.q;
+  V3 coord = (R.o + (R.t * R.d)) - v3(I.qx, I.qy, I.qz);
   float event_density = P.med.scale * density_at<LAYOUT>(P.med, I, coord);
   if (COUNT) ++C.dens;
   bool go_on = (R.t <= R.dist);
@@ -351,7 +345,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   LaneCounters C;
   const unsigned long long per_tile = P.path_end - P.path_begin;
   const unsigned long long total = per_tile * P.n_launch_tiles;
-  const TrackInv I = make_track_inv(P.med);
+  const TrackInv& I = P.inv;
   bool exhausted = false;
 
   for (;;) {
@@ -441,7 +435,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   LaneCounters C;
   const unsigned long long per_tile = P.path_end - P.path_begin;
   const unsigned long long total = per_tile * P.n_launch_tiles;
-  const TrackInv I = make_track_inv(P.med);
+  const TrackInv& I = P.inv;
 
   {  // all slots start idle
     PathRegs<Rng> R;
@@ -567,7 +561,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   LaneCounters C;
   const unsigned long long per_tile = P.path_end - P.path_begin;
   const unsigned long long total = per_tile * P.n_launch_tiles;
-  const TrackInv I = make_track_inv(P.med);
+  const TrackInv& I = P.inv;
 
   // all slots start idle, queued on the IDLE queue (key 3)
   for (unsigned i = threadIdx.x; i < N; i += blockDim.x) {
@@ -599,25 +593,29 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     // first and reading afterwards would let a fast warp wrap the ring over them.)
     int key = -1;
     unsigned h = 0, n = 0;
-    if (lane == 0) {
-      unsigned best = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        unsigned hk = ld_volatile_u32(&s_ctl.head[k]);
-        unsigned c = ld_volatile_u32(&s_ctl.tail[k]) - hk;
-        if ((int)c > (int)best) best = c, key = k, h = hk;
+    {
+      // lanes 0..3 each inspect one queue; the fullest wins (ties -> lowest key)
+      unsigned hk = 0, c = 0;
+      if (lane < 4) {
+        hk = ld_volatile_u32(&s_ctl.head[lane]);
+        c = ld_volatile_u32(&s_ctl.tail[lane]) - hk;
       }
+      unsigned c1 = __shfl_sync(FULL, c, 1), c2 = __shfl_sync(FULL, c, 2), c3 = __shfl_sync(FULL, c, 3);
+      unsigned c0 = __shfl_sync(FULL, c, 0);
+      unsigned best = c0;
+      key = c0 ? 0 : -1;
+      if (c1 > best) best = c1, key = 1;
+      if (c2 > best) best = c2, key = 2;
+      if (c3 > best) best = c3, key = 3;
+      h = __shfl_sync(FULL, hk, key < 0 ? 0 : key);
       n = best < 32u ? best : 32u;
     }
-    key = __shfl_sync(FULL, key, 0);
     if (key < 0) {
       unsigned nd = lane == 0 ? ld_volatile_u32(&s_ctl.n_done) : 0u;
       if (__shfl_sync(FULL, nd, 0) >= N) break;
       __nanosleep(100);
       continue;
     }
-    h = __shfl_sync(FULL, h, 0);
-    n = __shfl_sync(FULL, n, 0);
     __threadfence_block();
     const bool mine = lane < n;
     unsigned slot = 0;
@@ -771,11 +769,11 @@ __global__ void k_rng_kat(const int32_t* seeds, int n_seeds, int n, uint32_t* wo
 }
 
 template <int LAYOUT>
-__global__ void k_debug_lookup(MediumParams m, const float* p, int n, float* dens, float* alb) {
+__global__ void k_debug_lookup(MediumParams m, TrackInv inv, const float* p, int n, float* dens, float* alb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V3 c = v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
-  dens[i] = density_at<LAYOUT>(m, make_track_inv(m), c);
+  dens[i] = density_at<LAYOUT>(m, inv, c);
   V3 a = albedo_lookup<LAYOUT>(m, c);
   alb[3 * i] = a.x, alb[3 * i + 1] = a.y, alb[3 * i + 2] = a.z;
 }

@@ -544,6 +544,84 @@ struct QueueCtl {
 
 CVR_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
 
+// Write the lanes in `mask` back to their slots and enqueue every slot on the queue of
+// its new state (warp-aggregated reserve -> write -> ordered commit); finished slots
+// (S_DONE) are only counted.  Must be called by all 32 lanes.
+template <unsigned N>
+CVR_DEV void q_retire(PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl& ctl, bool in_mask, unsigned slot,
+                      const PathRegs<Xorwow>& R, unsigned lane) {
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane_lt = (1u << lane) - 1u;
+  if (in_mask) slot_store(s_slot[slot], R);
+  const int nk = in_mask ? sort_key(R.state) : 5;
+  unsigned my_p = 0, commit_mask = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned m = __ballot_sync(FULL, nk == k);
+    if (m) {
+      int leader = __ffs(m) - 1;
+      unsigned p = 0;
+      if ((int)lane == leader) p = atomicAdd(&ctl.resv[k], (unsigned)__popc(m));
+      p = __shfl_sync(FULL, p, leader);
+      if (nk == k) s_q[k][(p + __popc(m & lane_lt)) & (N - 1)] = (uint16_t)slot;
+      if ((int)lane == leader) my_p = p, commit_mask = m;
+    }
+  }
+  unsigned done_m = __ballot_sync(FULL, nk == 4);
+  // every lane's slot + queue stores must be visible before ANY leader publishes them:
+  // fence my own stores, then order the warp (lanes do not run in lock step)
+  __threadfence_block();
+  __syncwarp();
+  if (commit_mask) {
+    // ordered commit: our entries become poppable after every earlier reservation
+    const unsigned cnt = (unsigned)__popc(commit_mask);
+    while (atomicCAS(&ctl.tail[nk], my_p, my_p + cnt) != my_p) {
+    }
+  }
+  if (done_m && lane == 0) atomicAdd(&ctl.n_done, (unsigned)__popc(done_m));
+  __syncwarp();
+}
+
+// Pop up to popc(want) slot ids from queue `key` into the lanes of `want` and load the
+// paths.  The lanes READ their candidate entries first and only then lane 0 claims them
+// with a CAS on the pop cursor: entries in [head, tail) are live and cannot be
+// overwritten (a queue never holds more than N slots), so a successful CAS proves the
+// ids read were the ones claimed.  (Claiming first and reading afterwards lets a fast
+// warp wrap the ring over them.)  Returns the mask of lanes that received a path.
+template <unsigned N>
+CVR_DEV unsigned q_pop_into(const PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl& ctl, int key, unsigned want,
+                            unsigned lane, unsigned& slot, PathRegs<Xorwow>& R) {
+  const unsigned FULL = 0xffffffffu;
+  const unsigned rank = __popc(want & ((1u << lane) - 1u));
+  const bool wanted = (want >> lane) & 1u;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    unsigned h = 0, c = 0;
+    if (lane == 0) {
+      h = ld_volatile_u32(&ctl.head[key]);
+      c = ld_volatile_u32(&ctl.tail[key]) - h;
+    }
+    h = __shfl_sync(FULL, h, 0);
+    c = __shfl_sync(FULL, c, 0);
+    unsigned n = min(c, (unsigned)__popc(want));
+    if (n == 0) return 0u;
+    __threadfence_block();
+    const bool take = wanted && rank < n;
+    unsigned cand = 0;
+    if (take) cand = *(volatile uint16_t*)&s_q[key][(h + rank) & (N - 1)];
+    int ok = 0;
+    if (lane == 0) ok = atomicCAS(&ctl.head[key], h, h + n) == h;
+    if (__shfl_sync(FULL, ok, 0)) {
+      __threadfence_block();
+      if (take) {
+        slot = cand;
+        slot_load(s_slot[slot], R);
+      }
+      return __ballot_sync(FULL, take);
+    }
+  }
+  return 0u;
+}
+
 template <int RNGM, int LAYOUT, bool COUNT>
 __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     k_volpt_queued(const __grid_constant__ KernelParams P) {
@@ -552,7 +630,6 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   static_assert((N & (N - 1)) == 0, "CVR_QSLOTS must be a power of two");
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lane_lt = (1u << lane) - 1u;
 
   __shared__ PathSlot s_slot[N];
   __shared__ uint16_t s_q[4][N];
@@ -585,30 +662,21 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
   __syncthreads();
 
   for (;;) {
-    // ---------------------------------------------------------------- pop a batch
-    // lane 0 picks the fullest queue; the lanes READ their candidate entries first and
-    // only then lane 0 claims them with a CAS on the pop cursor.  Entries in
-    // [head, tail) are live and cannot be overwritten (a queue never holds more than N
-    // slots), so a successful CAS proves the ids read were the ones claimed.  (Claiming
-    // first and reading afterwards would let a fast warp wrap the ring over them.)
+    // ---------------------------------------------------------------- choose a queue
+    // lanes 0..3 each inspect one queue; the fullest wins (ties -> lowest key).
+    // (Measured alternatives, hetvol 1024^2: "full event batches first" -11 %,
+    // in-place refill of finished tracking lanes -28 %: see DESIGN.md.)
     int key = -1;
-    unsigned h = 0, n = 0;
     {
-      // lanes 0..3 each inspect one queue; the fullest wins (ties -> lowest key)
-      unsigned hk = 0, c = 0;
-      if (lane < 4) {
-        hk = ld_volatile_u32(&s_ctl.head[lane]);
-        c = ld_volatile_u32(&s_ctl.tail[lane]) - hk;
-      }
-      unsigned c1 = __shfl_sync(FULL, c, 1), c2 = __shfl_sync(FULL, c, 2), c3 = __shfl_sync(FULL, c, 3);
-      unsigned c0 = __shfl_sync(FULL, c, 0);
+      unsigned c = 0;
+      if (lane < 4) c = ld_volatile_u32(&s_ctl.tail[lane]) - ld_volatile_u32(&s_ctl.head[lane]);
+      unsigned c0 = __shfl_sync(FULL, c, 0), c1 = __shfl_sync(FULL, c, 1), c2 = __shfl_sync(FULL, c, 2),
+               c3 = __shfl_sync(FULL, c, 3);
       unsigned best = c0;
       key = c0 ? 0 : -1;
       if (c1 > best) best = c1, key = 1;
       if (c2 > best) best = c2, key = 2;
       if (c3 > best) best = c3, key = 3;
-      h = __shfl_sync(FULL, hk, key < 0 ? 0 : key);
-      n = best < 32u ? best : 32u;
     }
     if (key < 0) {
       unsigned nd = lane == 0 ? ld_volatile_u32(&s_ctl.n_done) : 0u;
@@ -616,76 +684,43 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
       __nanosleep(100);
       continue;
     }
-    __threadfence_block();
-    const bool mine = lane < n;
     unsigned slot = 0;
-    if (mine) slot = *(volatile uint16_t*)&s_q[key][(h + lane) & (N - 1)];
-    int ok = 0;
-    if (lane == 0) ok = atomicCAS(&s_ctl.head[key], h, h + n) == h;
-    if (!__shfl_sync(FULL, ok, 0)) continue;  // somebody else popped first: start over
-    __threadfence_block();
-
     PathRegs<Rng> R;
     R.state = S_DONE;
-    if (mine) slot_load(s_slot[slot], R);
+    unsigned got = q_pop_into<N>(s_slot, s_q, s_ctl, key, FULL, lane, slot, R);
+    if (!got) continue;  // somebody else emptied it first: start over
+    bool have = (got >> lane) & 1u;
 
     // ---------------------------------------------------------------- event of this batch
     if (key == 3) {
-      unsigned idle = __ballot_sync(FULL, mine && R.state == S_IDLE);
+      unsigned idle = __ballot_sync(FULL, have && R.state == S_IDLE);
       bool exhausted = ld_volatile_u32((const unsigned int*)&s_ctl.exhausted) != 0u;
       bool was = exhausted;
       if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
       if (exhausted && !was && lane == 0) s_ctl.exhausted = 1;
     } else if (key == 1) {
-      if (mine) do_scatter<LAYOUT, COUNT>(P, R, C);
+      if (have) do_scatter<LAYOUT, COUNT>(P, R, C);
     } else if (key == 2) {
-      if (mine) do_boundary(P, R);
+      if (have) do_boundary(P, R);
     }
-    if (R.state == S_ISECT) do_isect<COUNT>(P, R, C);
+    if (have && R.state == S_ISECT) do_isect<COUNT>(P, R, C);
 
     // ---------------------------------------------------------------- Woodcock steps
     for (int it = 0; it < P.track_steps; ++it) {
-      unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+      unsigned trk = __ballot_sync(FULL, have && R.state == S_TRACK);
       if (trk == 0) break;
       if (it > 0 && __popc(trk) < P.track_min_lanes) {
         // few lanes left: requeue them so they merge into a full batch -- unless
         // nobody else is queued for tracking
-        unsigned waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
+        unsigned waiting = 0;
+        if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
         if (__shfl_sync(FULL, waiting, 0) != 0u) break;
       }
-      if (R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
+      if (have && R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
     }
 
     // ---------------------------------------------------------------- write back + push
-    if (mine) slot_store(s_slot[slot], R);
-    const int nk = mine ? sort_key(R.state) : 5;
-    unsigned my_p = 0, commit_mask = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      unsigned m = __ballot_sync(FULL, nk == k);
-      if (m) {
-        int leader = __ffs(m) - 1;
-        unsigned p = 0;
-        if ((int)lane == leader) p = atomicAdd(&s_ctl.resv[k], (unsigned)__popc(m));
-        p = __shfl_sync(FULL, p, leader);
-        if (nk == k) s_q[k][(p + __popc(m & lane_lt)) & (N - 1)] = (uint16_t)slot;
-        if ((int)lane == leader) my_p = p, commit_mask = m;
-      }
-    }
-    unsigned done_m = __ballot_sync(FULL, nk == 4);
-    // every lane's slot + queue stores must be visible before ANY leader publishes them:
-    // fence my own stores, then order the warp (lanes do not run in lock step)
-    __threadfence_block();
-    __syncwarp();
-    if (commit_mask) {
-      // ordered commit: our entries become poppable after every earlier reservation
-      const int k = nk;
-      const unsigned cnt = (unsigned)__popc(commit_mask);
-      while (atomicCAS(&s_ctl.tail[k], my_p, my_p + cnt) != my_p) {
-      }
-    }
-    if (done_m && lane == 0) atomicAdd(&s_ctl.n_done, (unsigned)__popc(done_m));
-    __syncwarp();
+    q_retire<N>(s_slot, s_q, s_ctl, have, slot, R, lane);
   }
   flush_counters<COUNT>(P, C, lane);
 }

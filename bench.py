@@ -213,13 +213,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     d_img = torch.zeros((RES, RES, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    from cudavolumerenderer_b200.distributed import render_sharded, spp_shard
+
+    first, count = spp_shard(total_spp, rank, world)
+
     def step_device():
         flush.fill_(1)  # L2 flush between timed iterations
         kl.setSeed(0)
-        kl.renderImage((RES, RES), (1, 1), total_spp, fov_x=sc.fov_x, sample_first=SPP * rank,
-                       sample_count=SPP, d_image=d_img.data_ptr(), host_image=None)
-        if dist is not None:
-            dist.all_reduce(d_img)  # sum of the per-rank partial means -> the image
+        # this rank's 64 sample indices of the 64*N-spp image, then ONE NCCL all-reduce
+        render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x)
 
     def barrier():
         if dist is not None:
@@ -262,9 +264,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if dist is None:
             kl.renderImage((RES, RES), (1, 1), total_spp, fov_x=sc.fov_x, host_image=host_img.numpy())  # D2H inside
         else:
-            kl.renderImage((RES, RES), (1, 1), total_spp, fov_x=sc.fov_x, sample_first=SPP * rank,
-                           sample_count=SPP, d_image=d_img.data_ptr(), host_image=None)
-            dist.all_reduce(d_img)
+            render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x)
             host_img.copy_(d_img, non_blocking=False)
 
     step_e2e()

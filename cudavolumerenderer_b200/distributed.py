@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing: one process per GPU, volume replicated, work sharded by image
+tiles or by sample index, ONE collective per render (sum of the resolved framebuffers)
+through torch.distributed (NCCL on GPUs; gloo in the CPU tests).  SURVEY.md section 8(e).
+
+Sharding rules (pure functions, tested on CPU):
+  tiles: rank r renders tiles k = r, r+G, ... of the reference's tile list -> disjoint
+         pixels, the image does not depend on G.
+  spp:   rank r renders sample indices [first, first+count) of every pixel; stream ids
+         are seed + sample*npix + pixel, so the multiset of paths equals the 1-GPU run.
+Every rank resolves with scale = TOTAL iterations, so the sum over ranks is the image.
+"""
+from __future__ import annotations
+
+
+def spp_shard(total_spp: int, rank: int, world: int) -> tuple[int, int]:
+    """(first, count) of the sample indices rank `rank` renders; remainders go to the
+    low ranks so that counts differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, rem = divmod(total_spp, world)
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+def tile_shard(n_tiles: int, rank: int, world: int) -> list[int]:
+    """Global tile indices of rank `rank` (interleaved: k = rank (mod world))."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_tiles, world))
+
+
+def render_sharded(launcher, res, n_tiles, iterations: int, mode: str, d_image, fov_x: float = 0.7,
+                   inv_view=None, fuse_tiles: bool = True):
+    """Render this rank's share into the torch tensor `d_image` (H, W, 4 float32, on the
+    launcher's device; zero-filled here first) and all-reduce it.  Returns d_image."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    d_image.zero_()
+    kw = dict(fov_x=fov_x, inv_view=inv_view, d_image=d_image.data_ptr(), host_image=None, fuse_tiles=fuse_tiles)
+    if mode == "spp":
+        first, count = spp_shard(iterations, rank, world)
+        if count:
+            launcher.renderImage(res, n_tiles, iterations, sample_first=first, sample_count=count, **kw)
+    elif mode == "tiles":
+        launcher.renderImage(res, n_tiles, iterations, tile_first=rank, tile_stride=world, **kw)
+    else:
+        raise ValueError("mode must be 'spp' or 'tiles'")
+    if world > 1:
+        dist.all_reduce(d_image)
+    return d_image

@@ -1,0 +1,157 @@
+// CudaVolPath.h -- tile scheduler + progressive renderer of the drop-in host layer.
+//
+// Mirrors TilingConfig (Config.h:61-78), Buffer2D (Buffer.h:54-130),
+// AbstractRenderer / AbstractProgressiveRenderer (AbstractRenderer.h:8-24),
+// CudaVolPath<Launcher> (CudaVolPath.h:34-102, CudaVolPath.cpp) and the factory switch
+// (RendererFactory.h:37-115).  The renderer drives a launcher call by call in the
+// reference's order; the caller-owned tile buffer is plain cudaMalloc memory.
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include "RenderKernelLauncher.h"
+
+namespace cvrhost {
+
+struct TilingConfig {  // Config.h:61-78
+  uint2 n_tiles{1, 1};
+  uint2 tile_dim{};
+  uint2 resolution{400, 400};
+  explicit TilingConfig(uint2 res = {400, 400}, uint2 tiles = {1, 1}) : n_tiles(tiles), resolution(res) {
+    tile_dim.x = (uint32_t)(int)std::ceil((double)(resolution.x / n_tiles.x));  // integer division: floors (Q6)
+    tile_dim.y = (uint32_t)(int)std::ceil((double)(resolution.y / n_tiles.y));
+  }
+};
+
+struct Buffer2D {  // Buffer.h:54-130 (float4 host image view)
+  void* data = nullptr;
+  size_t width = 0, width_bytes = 0, height = 0, pitch_bytes = 0;
+};
+inline Buffer2D make_buffer2D_float4(float* data, size_t w, size_t h) {
+  return {data, w, w * 16, h, w * 16};
+}
+
+class AbstractRenderer {
+ public:
+  virtual ~AbstractRenderer() = default;
+  virtual void render(Buffer2D buffer_out) = 0;
+};
+
+class AbstractProgressiveRenderer : public AbstractRenderer {
+ public:
+  virtual void initRendering() = 0;
+  virtual void runIterations() = 0;
+  virtual void setNIterations(uint32_t n) = 0;
+  virtual bool imageComplete() = 0;
+  virtual void getImage(Buffer2D buffer_out) = 0;
+};
+
+inline void cuda_ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class VolPathKernelLauncher>
+class CudaVolPath : public AbstractProgressiveRenderer {
+  TilingConfig tiling_config_;
+  uint32_t iterations_;
+  Scene scene_;
+  uint32_t current_iteration_ = 0;
+  std::vector<uint2> tiles_;
+  size_t current_tile_ = 0;
+  void* d_output_ = nullptr;  // tile accumulation buffer (float4)
+  void* d_image_ = nullptr;   // resolved full image (float4)
+  VolPathKernelLauncher kernel_launcher_;
+
+  void initTileArray() {  // CudaVolPath.cpp:12-29
+    uint32_t n = tiling_config_.n_tiles.x * tiling_config_.n_tiles.y;
+    std::vector<uint32_t> org(2 * (size_t)n);
+    uint32_t dim[2];
+    cvr_tile_table(tiling_config_.resolution.x, tiling_config_.resolution.y, tiling_config_.n_tiles.x,
+                   tiling_config_.n_tiles.y, dim, org.data());
+    tiles_.resize(n);
+    for (uint32_t i = 0; i < n; ++i) tiles_[i] = {org[2 * i], org[2 * i + 1]};
+    current_tile_ = 0;
+  }
+
+ public:
+  CudaVolPath(const Scene& scene, TilingConfig tiling, uint32_t iterations, int device = 0)
+      : tiling_config_(tiling), iterations_(iterations), scene_(scene), kernel_launcher_(device) {
+    // constructor order of CudaVolPath.cpp:31-59
+    initTileArray();
+    auto rtv = scene_.getCamera()->getRasterToView();
+    kernel_launcher_.copyRasterToView(rtv[0], rtv[1]);
+    kernel_launcher_.setResolution(tiling_config_.tile_dim);
+    kernel_launcher_.copyPixelIndexRange((float)tiling_config_.resolution.x, (float)tiling_config_.resolution.y);
+    kernel_launcher_.init();
+    size_t tile_px = (size_t)tiling_config_.tile_dim.x * tiling_config_.tile_dim.y;
+    cuda_ck(cudaMalloc(&d_output_, tile_px * 16), "cudaMalloc tile");  // allocateDeviceMemory :211-232
+    cuda_ck(cudaMalloc(&d_image_, (size_t)tiling_config_.resolution.x * tiling_config_.resolution.y * 16), "cudaMalloc image");
+    kernel_launcher_.setOutputPtr(d_output_);
+    kernel_launcher_.allocateDeviceMemory();
+    kernel_launcher_.setScene(scene_);  // initDeviceScene :87-115
+  }
+  ~CudaVolPath() override {
+    cudaDeviceSynchronize();
+    cudaFree(d_output_);
+    cudaFree(d_image_);
+  }
+  VolPathKernelLauncher& launcher() { return kernel_launcher_; }
+
+  void setNIterations(uint32_t n) override {
+    iterations_ = n;
+    kernel_launcher_.setNIterations(n);
+  }
+  void initRendering() override {  // initCamera + initRenderState (:66-85, :202-208)
+    kernel_launcher_.copyInvViewMatrix(scene_.getCamera()->getInvViewMatrix(), 48);
+    current_iteration_ = 0;
+    size_t tile_px = (size_t)tiling_config_.tile_dim.x * tiling_config_.tile_dim.y;
+    cuda_ck(cudaMemset(d_output_, 0, tile_px * 16), "cudaMemset");
+    current_tile_ = 0;
+  }
+  bool imageComplete() override { return current_tile_ == tiles_.size(); }
+  void runIterations() override {  // :248-280
+    if (current_tile_ == tiles_.size()) current_tile_ = 0;
+    if (current_tile_ == 0) current_iteration_ += kernel_launcher_.getNIterations();
+    kernel_launcher_.copyOffset(tiles_[current_tile_]);
+    kernel_launcher_.launchRender();
+    ++current_tile_;
+  }
+  void getImage(Buffer2D out) override {  // :282-295 + prepareForNextIterations :188-200
+    uint2 tile_start = tiles_[current_tile_ - 1];
+    uint2 td = tiling_config_.tile_dim, full = tiling_config_.resolution;
+    // intended transfer semantics (the reference's delegate is broken at HEAD, Q13): every
+    // float of the tile divided by current_iteration_, copied at the tile origin
+    kernel_launcher_.resolveTile(d_output_, td, d_image_, full, tile_start, (float)current_iteration_);
+    kernel_launcher_.reset();  // sync + seed advance
+    size_t off = ((size_t)tile_start.y * full.x + tile_start.x) * 16;
+    cuda_ck(cudaMemcpy2D((char*)out.data + (size_t)tile_start.y * out.pitch_bytes + (size_t)tile_start.x * 16,
+                         out.pitch_bytes, (char*)d_image_ + off, (size_t)full.x * 16, (size_t)td.x * 16, td.y,
+                         cudaMemcpyDeviceToHost), "cudaMemcpy2D");
+    if (tiles_.size() != 1) {  // with one tile the buffer keeps accumulating
+      cuda_ck(cudaMemset(d_output_, 0, (size_t)td.x * td.y * 16), "cudaMemset");
+    }
+  }
+  void render(Buffer2D out) override {  // :338-347
+    setNIterations(iterations_);
+    initRendering();
+    while (!imageComplete()) {
+      runIterations();
+      getImage(out);
+    }
+  }
+};
+
+// RendererFactory::createRenderer (RendererFactory.h:13-22,37-115): kernel name -> renderer
+inline std::unique_ptr<AbstractProgressiveRenderer> createRenderer(const std::string& kernel, const Scene& scene,
+                                                                   TilingConfig tiling, uint32_t iterations,
+                                                                   int device = 0) {
+  if (kernel == "naiveSK") return std::make_unique<CudaVolPath<NaiveVolPTsk>>(scene, tiling, iterations, device);
+  if (kernel == "regenerationSK") return std::make_unique<CudaVolPath<RegenerationVolPTsk>>(scene, tiling, iterations, device);
+  if (kernel == "streamingSK") return std::make_unique<CudaVolPath<StreamingVolPTsk>>(scene, tiling, iterations, device);
+  throw std::runtime_error("kernel '" + kernel + "' is not available in this build (naiveSK | regenerationSK | streamingSK)");
+}
+
+}  // namespace cvrhost

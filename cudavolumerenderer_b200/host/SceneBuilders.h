@@ -1,0 +1,258 @@
+// SceneBuilders.h -- the reference's scene loaders behind SceneBuilder, dependency-free.
+//
+//  RawSceneBuilder   RawSceneBuilder.h:35-140   32^3 uint8 .raw + transfer function
+//  XmlSceneBuilder   XmlSceneBuilder.h:39-266   Mitsuba scene XML subset + VOL v3 grids
+//                    (no pugixml: the handful of attributes the reference reads are
+//                    extracted with a small tag scanner)
+//  VDBSceneBuilder   VDBSceneBuilder.h:40-80    needs an OpenVDB/blosc decoder, which this
+//                    image does not have: reports that instead of guessing
+//  SynthSceneBuilder "synth:<name>" procedural stand-ins (csrc/cvr_synth.cpp)
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <optional>
+#include <sstream>
+
+#include "Scene.h"
+
+namespace cvrhost {
+
+class RawSceneBuilder : public SceneBuilder {
+  std::shared_ptr<Camera> camera_;
+  HostMedium medium_;
+
+ public:
+  explicit RawSceneBuilder(const std::string& filename) {
+    const uint32_t n = 32;  // RawSceneBuilder.h:36: hard-coded 32^3 uint8
+    std::vector<unsigned char> raw((size_t)n * n * n);
+    FILE* fp = fopen(filename.c_str(), "rb");
+    if (!fp) throw std::runtime_error("Error opening file '" + filename + "'");
+    size_t got = fread(raw.data(), 1, raw.size(), fp);
+    fclose(fp);
+    if (got != raw.size()) throw std::runtime_error("Error reading file '" + filename + "' (expected 32768 bytes)");
+    auto& den = medium_.density_volume;
+    den.nx = den.ny = den.nz = n;
+    den.data.resize(raw.size());
+    float mx = 0;
+    for (size_t i = 0; i < raw.size(); ++i) {
+      den.data[i] = raw[i];
+      mx = std::fmax(den.data[i], mx);
+    }
+    for (auto& v : den.data) v /= mx;  // RawSceneBuilder.h:62-64
+    medium_.albedo_volume = albedoFromDensity(den);
+    medium_.max_density = 1;  // :68
+    medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+    medium_.scale = 40;  // :78
+    camera_ = std::make_shared<Camera>();
+  }
+  std::shared_ptr<Camera> getCamera() override { return camera_; }
+  HostMedium getMedium() override { return medium_; }
+
+  // RawSceneBuilder.h:95-139: 100-entry two-ramp transfer function, index ceil(d * 99)
+  static Volume<4> albedoFromDensity(const Volume<1>& den) {
+    const float len = 100.f;
+    std::vector<std::array<float, 3>> tf;
+    float sr = 0.02f, sg = 0.2f, sb = 0.02f, er = 1.f, eg = 0.02f, eb = 0.02f;
+    for (int i = 0; i < len * 1.f / 5.f; i++)
+      tf.push_back({sr + (i * (er - sr) / len), sg + (i * (eg - sg) / len), sb + (i * (eb - sb) / len)});
+    sr = er, sg = eg, sb = eb, er = 0.0f, eg = 0.02f, eb = 1.0f;
+    for (int i = 0; i < len * 4.f / 5.f; i++)
+      tf.push_back({sr + (i * (er - sr) / len), sg + (i * (eg - sg) / len), sb + (i * (eb - sb) / len)});
+    Volume<4> a;
+    a.nx = den.nx, a.ny = den.ny, a.nz = den.nz;
+    a.data.resize(den.voxels() * 4);
+    for (size_t i = 0; i < den.voxels(); ++i) {
+      float v = den.data[i] * (tf.size() - 1);
+      const auto& c = tf[(size_t)std::ceil(v)];
+      a.data[4 * i] = c[0], a.data[4 * i + 1] = c[1], a.data[4 * i + 2] = c[2], a.data[4 * i + 3] = 1.f;
+    }
+    return a;
+  }
+};
+
+class XmlSceneBuilder : public SceneBuilder {
+  std::shared_ptr<Camera> camera_;
+  HostMedium medium_;
+  // members overwritten by every loadVolFile call, as in the reference (Q3)
+  uint32_t vol_nx_ = 0, vol_ny_ = 0, vol_nz_ = 0;
+  float3 box_min_, box_max_;
+
+  // value of attribute `attr` inside the first tag that starts at or after `from` and
+  // matches <tag ... name="name" ...>
+  static std::optional<std::string> attrOf(const std::string& xml, const std::string& tag, const std::string& name,
+                                           const std::string& attr, size_t from = 0, size_t until = std::string::npos) {
+    size_t pos = from;
+    while ((pos = xml.find("<" + tag, pos)) != std::string::npos && pos < until) {
+      size_t end = xml.find('>', pos);
+      if (end == std::string::npos) break;
+      std::string t = xml.substr(pos, end - pos);
+      if (name.empty() || t.find("name=\"" + name + "\"") != std::string::npos) {
+        size_t a = t.find(attr + "=\"");
+        if (a != std::string::npos) {
+          a += attr.size() + 2;
+          return t.substr(a, t.find('"', a) - a);
+        }
+      }
+      pos = end;
+    }
+    return std::nullopt;
+  }
+
+  // XmlSceneBuilder.h:195-266: "VOL", u8 version 3, i32 type, 3 x i32 dims, i32 channels,
+  // 6 x f32 AABB, fp32 payload (x fastest, channels interleaved)
+  std::vector<float> loadVolFile(const std::string& filename, int expect_channels) {
+    std::ifstream s(filename, std::ios::binary | std::ios::ate);
+    if (!s) throw std::runtime_error("Error opening file '" + filename + "'");
+    std::streamoff size = s.tellg();
+    s.seekg(0);
+    char hdr[3];
+    if (!s.read(hdr, 3)) throw std::runtime_error("Error reading file '" + filename + "'");
+    if (hdr[0] != 'V' || hdr[1] != 'O' || hdr[2] != 'L')
+      throw std::runtime_error("Invalid volume data file (incorrect header identifier)");
+    uint8_t version = 0;
+    s.read((char*)&version, 1);
+    if (version != 3) throw std::runtime_error("Invalid volume data file (incorrect file version)");
+    int32_t type = 0, dims[3] = {0, 0, 0}, channels = 0;
+    s.read((char*)&type, 4);
+    s.read((char*)dims, 12);
+    s.read((char*)&channels, 4);
+    float bb[6];
+    s.read((char*)bb, 24);
+    vol_nx_ = dims[0], vol_ny_ = dims[1], vol_nz_ = dims[2];
+    box_min_ = {bb[0], bb[1], bb[2]}, box_max_ = {bb[3], bb[4], bb[5]};
+    if (channels != expect_channels) throw std::runtime_error("Unsupported volume type (channel count)");
+    size -= 3 + 1 + 4 + 12 + 4 + 24;
+    std::vector<float> data((size_t)size / sizeof(float));
+    if (!s.read((char*)data.data(), (std::streamsize)(data.size() * sizeof(float))))
+      throw std::runtime_error("Error reading data from file '" + filename + "'");
+    if (data.size() < (size_t)dims[0] * dims[1] * dims[2] * channels)
+      throw std::runtime_error("Volume data size does not match grid resolution");
+    return data;
+  }
+
+ public:
+  explicit XmlSceneBuilder(const std::string& xml_path) {
+    std::ifstream f(xml_path);
+    if (!f) throw std::invalid_argument("File was not found: " + xml_path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string xml = ss.str();
+    std::string base = xml_path;
+    size_t slash = base.find_last_of("/\\");
+    base = slash == std::string::npos ? "" : base.substr(0, slash + 1);
+
+    size_t med = xml.find("type=\"heterogeneous\"");
+    if (med == std::string::npos) throw std::invalid_argument("Internal error occurred");
+    size_t med_end = xml.find("</medium>", med);
+    auto volume_file = [&](const std::string& which) {
+      size_t v = xml.find("name=\"" + which + "\"", med);
+      if (v == std::string::npos || v > med_end) throw std::invalid_argument("Internal error occurred");
+      size_t tag = xml.rfind("<volume", v);
+      std::string t = xml.substr(tag, xml.find('>', tag) - tag);
+      if (t.find("type=\"gridvolume\"") == std::string::npos) throw std::invalid_argument("Internal error occurred");
+      // the value of the first <string> child (XmlSceneBuilder.h:64-82)
+      auto val = attrOf(xml, "string", "", "value", v, xml.find("</volume>", v));
+      if (!val) throw std::invalid_argument("Internal error occurred");
+      return base + *val;
+    };
+    std::string density_file = volume_file("density"), albedo_file = volume_file("albedo");
+    auto scale = attrOf(xml, "float", "scale", "value", med, med_end);
+    if (!scale) throw std::invalid_argument("Internal error occurred");
+
+    // density first, albedo second: the medium box ends up being the ALBEDO grid's (Q3)
+    std::vector<float> den = loadVolFile(density_file, 1);
+    auto& dv = medium_.density_volume;
+    dv.nx = vol_nx_, dv.ny = vol_ny_, dv.nz = vol_nz_;
+    den.resize(dv.voxels());
+    float mx = 0;
+    for (float v : den) mx = std::max(std::min(1.0f, v), mx);  // XmlSceneBuilder.h:187
+    medium_.max_density = mx;
+    dv.data = std::move(den);
+    std::vector<float> alb = loadVolFile(albedo_file, 3);
+    auto& av = medium_.albedo_volume;
+    av.nx = vol_nx_, av.ny = vol_ny_, av.nz = vol_nz_;
+    av.data.resize(av.voxels() * 4);
+    for (size_t i = 0; i < av.voxels(); ++i) {
+      av.data[4 * i] = alb[3 * i], av.data[4 * i + 1] = alb[3 * i + 1], av.data[4 * i + 2] = alb[3 * i + 2];
+      av.data[4 * i + 3] = 1.0f;
+    }
+    medium_.density_AABB = {box_min_, box_max_};
+    medium_.scale = std::stof(*scale);
+
+    // setupCamera (XmlSceneBuilder.h:122-152): film size + fov only; lookat is ignored (Q5)
+    size_t sensor = xml.find("<sensor");
+    int w = 400, h = 400;
+    float fov = 45.0f;
+    if (sensor != std::string::npos) {
+      size_t send = xml.find("</sensor>", sensor);
+      if (auto v = attrOf(xml, "float", "fov", "value", sensor, send)) fov = std::stof(*v);
+      auto ws = attrOf(xml, "integer", "width", "value", sensor, send), hs = attrOf(xml, "integer", "height", "value", sensor, send);
+      if (ws && hs) w = std::stoi(*ws), h = std::stoi(*hs);
+    }
+    camera_ = std::make_shared<Camera>(w, h, fov);
+  }
+  std::shared_ptr<Camera> getCamera() override { return camera_; }
+  HostMedium getMedium() override { return medium_; }
+};
+
+class VDBSceneBuilder : public SceneBuilder {
+ public:
+  explicit VDBSceneBuilder(const std::string& filename) {
+    throw std::runtime_error("Vdb scenes need an OpenVDB/blosc decoder, which is not available in this build: '" +
+                             filename + "' (convert the grid to Mitsuba VOL or use synth:manix)");
+  }
+  std::shared_ptr<Camera> getCamera() override { return nullptr; }
+  HostMedium getMedium() override { return {}; }
+};
+
+// procedural stand-ins for the LFS-stub payloads: "synth:bucky|hetvol|manix|fbm[:n]"
+class SynthSceneBuilder : public SceneBuilder {
+  std::shared_ptr<Camera> camera_;
+  HostMedium medium_;
+
+ public:
+  explicit SynthSceneBuilder(const std::string& spec) {
+    std::string name = spec.substr(spec.find(':') + 1);
+    uint32_t n = 0;
+    if (size_t c = name.find(':'); c != std::string::npos) {
+      n = (uint32_t)std::stoul(name.substr(c + 1));
+      name = name.substr(0, c);
+    }
+    uint32_t nx, ny, nz;
+    float fov = 0.7f;
+    bool want_albedo = true;
+    if (name == "bucky") {
+      nx = ny = nz = 32, medium_.scale = 40;
+      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+    } else if (name == "hetvol") {
+      nx = ny = 128, nz = 50, medium_.scale = 800, fov = 0.33f;
+      medium_.density_AABB = {{-0.64f, -0.64f, -0.25f}, {0.64f, 0.64f, 0.25f}};
+    } else if (name == "manix") {
+      nx = 256, ny = 230, nz = 256, medium_.scale = 100;
+      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+    } else if (name == "fbm") {
+      nx = ny = nz = n ? n : 256, medium_.scale = 100;
+      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+    } else {
+      throw std::invalid_argument("unknown synthetic scene '" + name + "'");
+    }
+    auto& dv = medium_.density_volume;
+    dv.nx = nx, dv.ny = ny, dv.nz = nz;
+    dv.data.resize(dv.voxels());
+    auto& av = medium_.albedo_volume;
+    if (want_albedo) {
+      av.nx = nx, av.ny = ny, av.nz = nz;
+      av.data.resize(av.voxels() * 4);
+    }
+    if (cvr_synth_volume(name.c_str(), (int32_t)nx, (int32_t)ny, (int32_t)nz, 0, dv.data.data(),
+                         want_albedo ? av.data.data() : nullptr, &medium_.max_density))
+      throw std::runtime_error("cvr_synth_volume failed for '" + name + "'");
+    camera_ = std::make_shared<Camera>(400, 400, fov);
+  }
+  std::shared_ptr<Camera> getCamera() override { return camera_; }
+  HostMedium getMedium() override { return medium_; }
+};
+
+}  // namespace cvrhost

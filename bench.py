@@ -248,7 +248,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         ms = float(t.item())
     paths_per_step = RES * RES * SPP * world
     value = paths_per_step * args.steps / ms / 1e3
-    img_mean = float(d_img[..., :3].mean().item())
+    rgb = d_img[..., :3]
+    nan_px = int(torch.isnan(rgb).any(dim=2).sum().item())  # the reference's own u == 1.0 GGX singularity
+    img_mean = float(torch.nanmean(rgb).item())
 
     # ---- end-to-end through the C ABI with host buffers
     pin_den = torch.from_numpy(sc.density).pin_memory()
@@ -328,7 +330,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "config": {"workload": WORKLOAD, "resolution": [RES, RES], "spp_per_gpu": SPP, "total_spp": total_spp,
                    "kernel": "regenerationSK", "rng": kl.getOption("rng"), "layout": kl.getOption("layout"),
                    "sharding": "spp" if world > 1 else "none", "l2": "flushed between steps (256 MiB write)",
-                   "image_mean": img_mean},
+                   "image_mean": img_mean, "nan_pixels": nan_px},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / n_e2e},

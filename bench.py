@@ -307,12 +307,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     except Exception:
         pass
     grid, block, regs = kl.launchShape()
+    # measured random-32-B-sector gather peak at this volume's device footprint (L2-resident here)
+    nz, ny, nx = sc.density.shape
+    footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 128)  # density + albedo cell8 layouts
+    gather_peak = kl.gatherRoofline(footprint, 512, 8)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_volpt", "peak_source": peak_src,
                 "kernel_ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
                 "density_lookups_per_s": ctr["density_lookups"] / (ctr["kernel_ms"] * 1e-3),
                 "kernel_share_of_step": ctr["kernel_ms"] / ms,
-                "launch": {"grid": grid, "block": block, "regs": regs}}
+                "launch": {"grid": grid, "block": block, "regs": regs},
+                "gather_roofline": {"what": "random 32-B-sector 256-bit gather microbenchmark at the volume's device footprint",
+                                    "footprint_bytes": footprint, "peak": gather_peak, "unit": "GB/s",
+                                    "frac": achieved / gather_peak}}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None

@@ -96,6 +96,7 @@ SYMBOLS = [
     ("cvr_trace_paths", C.c_int, [H, C.c_uint64, C.c_uint64, C.c_void_p]),
     ("cvr_rng_kat", C.c_int, [H, C.POINTER(C.c_int32), C.c_int, C.c_int, u32p, f32p]),
     ("cvr_debug_lookup", C.c_int, [H, f32p, C.c_int, f32p, f32p]),
+    ("cvr_gather_roofline", C.c_int, [H, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("cvr_synth_volume", C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, f32p, f32p, f32p]),
 ]
 

@@ -877,6 +877,44 @@ int cvr_rng_kat(cvr_handle h, const int32_t* seeds, int n_seeds, int n, uint32_t
   return 0;
 }
 
+int cvr_gather_roofline(cvr_handle h, uint64_t footprint_bytes, int loads_per_thread, int unroll, double* gbs) {
+  CVR_CHECK_HANDLE(h);
+  if (!gbs || footprint_bytes < 4096 || loads_per_thread < 1) return fail(h, "cvr_gather_roofline: bad arguments");
+  if (set_device(h)) return 1;
+  uint64_t n_cells = footprint_bytes / 32;
+  if (n_cells >= (1ull << 32)) n_cells = (1ull << 32) - 1;
+  float *d_cells, *d_sink;
+  CVR_CUDA(h, cudaMalloc(&d_cells, n_cells * 32));
+  CVR_CUDA(h, cudaMalloc(&d_sink, 4));
+  CVR_CUDA(h, cudaMemsetAsync(d_cells, 0, n_cells * 32, h->stream));
+  const int grid = h->sm_count * 8, block = 256;
+  loads_per_thread = (loads_per_thread + 7) / 8 * 8;
+  cudaEvent_t e0, e1;
+  CVR_CUDA(h, cudaEventCreate(&e0));
+  CVR_CUDA(h, cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms the caches / TLB
+    CVR_CUDA(h, cudaEventRecord(e0, h->stream));
+    if (unroll >= 8)
+      k_gather_bench<8><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);
+    else if (unroll >= 4)
+      k_gather_bench<4><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);
+    else
+      k_gather_bench<1><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);
+    CVR_CUDA(h, cudaGetLastError());
+    CVR_CUDA(h, cudaEventRecord(e1, h->stream));
+    CVR_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CVR_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+    double v = (double)grid * block * loads_per_thread * 32.0 / (ms * 1e-3) / 1e9;
+    if (rep > 0 && v > best) best = v;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(d_cells), cudaFree(d_sink);
+  *gbs = best;
+  return 0;
+}
+
 int cvr_debug_lookup(cvr_handle h, const float* p, int n, float* dens, float* alb) {
   CVR_CHECK_HANDLE(h);
   if (!h->scene_set) return fail(h, "cvr_debug_lookup before cvr_set_scene");

@@ -790,6 +790,33 @@ __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w,
   }
 }
 
+// ---------------------------------------------------------------- gather roofline
+// Random 32-byte-sector gather microbenchmark: every thread issues
+// `per_thread` independent 256-bit loads at hashed cell indices of a `n_cells`-cell
+// buffer, UNROLL in flight at a time; the sum defeats dead-code elimination.  This is
+// the measured "gather roofline" denominator for a given footprint (L2-resident or HBM).
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_gather_bench(const float* __restrict__ cells, uint32_t n_cells,
+                                                       int per_thread, float* sink) {
+  uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (int i = 0; i < per_thread; i += UNROLL) {
+    float v[UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      x = x * 1664525u + 1013904223u;
+      uint32_t h = x ^ (x >> 15);
+      h *= 0x2c1b3c6du;
+      h ^= h >> 12;
+      uint32_t cell = (uint32_t)(((unsigned long long)h * n_cells) >> 32);
+      ldg256(cells + 8 * (size_t)cell, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc += v[u][0] + v[u][7];
+  }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+
 // ---------------------------------------------------------------- debug kernels
 __global__ void k_rng_kat(const int32_t* seeds, int n_seeds, int n, uint32_t* words, float* uni) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

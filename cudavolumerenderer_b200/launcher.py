@@ -233,6 +233,13 @@ class VolPTKernelLauncher:
                                        w.ctypes.data_as(abi.u32p), u.ctypes.data_as(abi.f32p)), "rngKat")
         return w, u
 
+    def gatherRoofline(self, footprint_bytes: int, loads_per_thread: int = 256, unroll: int = 8) -> float:
+        """Measured random 32-byte-sector gather bandwidth (GB/s) at this footprint."""
+        g = C.c_double()
+        self._ck(self._lib.cvr_gather_roofline(self._h, footprint_bytes, loads_per_thread, unroll, C.byref(g)),
+                 "gatherRoofline")
+        return g.value
+
     def debugLookup(self, p01: np.ndarray):
         p = np.ascontiguousarray(p01, np.float32).reshape(-1, 3)
         d = np.zeros(len(p), np.float32)

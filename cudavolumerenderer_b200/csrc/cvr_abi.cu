@@ -41,7 +41,7 @@ struct cvr_renderer {
   // options
   int rng_mode = RNG_XORWOW_PATH;
   int layout = LAYOUT_CELL8;
-  int exact = 1;
+  int exact = 0;  // 0 = fused arithmetic (queued scheduler only), 1 = the reference's operation order
   int rr = 1;
   uint32_t max_bounces = 1u << 20;
   int block = CVR_BLOCK;
@@ -115,7 +115,7 @@ int fail(cvr_handle h, const char* fmt, ...) {
 
 typedef void (*kernel_fn)(const KernelParams);
 
-kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count) {
+kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1) {
 #define CVR_K(R, L)                                      \
   if (sched == 0 && rng_mode == R && layout == L)        \
     return count ? (kernel_fn)k_volpt<R, L, true> : (kernel_fn)k_volpt<R, L, false>;
@@ -134,9 +134,11 @@ kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count) {
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
 #undef CVR_K
-#define CVR_K(R, L)                                      \
-  if (sched == 2 && rng_mode == R && layout == L)        \
-    return count ? (kernel_fn)k_volpt_queued<R, L, true> : (kernel_fn)k_volpt_queued<R, L, false>;
+#define CVR_K(R, L)                                                                                    \
+  if (sched == 2 && rng_mode == R && layout == L) {                                                    \
+    if (exact) return count ? (kernel_fn)k_volpt_queued<R, L, true, false> : (kernel_fn)k_volpt_queued<R, L, false, false>; \
+    return count ? (kernel_fn)k_volpt_queued<R, L, true, true> : (kernel_fn)k_volpt_queued<R, L, false, true>;           \
+  }
   CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
   CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
@@ -172,7 +174,7 @@ int ensure_allocated(cvr_handle h) {
 
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact);
   if (!k) return fail(h, "no kernel for sched=%d rng=%d layout=%d (philox needs sched=lane)", h->sched, h->rng_mode, h->layout);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
@@ -209,6 +211,9 @@ void fill_track_inv(KernelParams& P) {
   I.rx = (float)(uint32_t)(m.dnx - 1), I.ry = (float)(uint32_t)(m.dny - 1), I.rz = (float)(uint32_t)(m.dnz - 1);
   I.nx = m.dnx, I.ny = m.dny, I.nz = m.dnz;
   I.sy = m.dnx + 1, I.sz = (uint32_t)(m.dnx + 1) * (uint32_t)(m.dny + 1);
+  I.nqrx = -I.qx * I.rx, I.nqry = -I.qy * I.ry, I.nqrz = -I.qz * I.rz;
+  I.sig_ratio = m.scale * I.inv_max_sigmat;
+  I.aix = 1.0f / ex, I.aiy = 1.0f / ey, I.aiz = 1.0f / ez;
 }
 
 // fills the per-launch part of the kernel parameters and launches
@@ -246,7 +251,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact);
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
@@ -387,8 +392,8 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
   } else if (k == "tracking") {
     if (v != "global") return fail(h, "tracking=%s is not available in this build (global only)", value);
   } else if (k == "exact") {
-    h->exact = atoi(value);
-    if (!h->exact) return fail(h, "exact=0 (fused arithmetic) is not available in this build");
+    h->exact = atoi(value) ? 1 : 0;
+    h->inited = false;
   } else if (k == "russian_roulette") {
     h->rr = atoi(value) ? 1 : 0;
   } else if (k == "max_bounces") {
@@ -441,7 +446,7 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "tracking")
     v = "global";
   else if (k == "exact")
-    v = std::to_string(h->exact);
+    v = std::to_string(h->sched == 2 ? h->exact : 1);
   else if (k == "russian_roulette")
     v = std::to_string(h->rr);
   else if (k == "max_bounces")

@@ -33,6 +33,10 @@ struct TrackInv {
   float rx, ry, rz;      // (float)(uint)(res - 1)
   uint32_t nx, ny, nz;   // density dims
   uint32_t sy, sz;       // cell strides (cell8) in cells
+  // fused ("exact=0") forms
+  float nqrx, nqry, nqrz;  // -q * r : grid coordinate = fma(p, r, nqr)
+  float sig_ratio;         // scale * inv_max_sigmat : accept test = density * sig_ratio < u
+  float aix, aiy, aiz;     // 1 / (box_max - box_min) for the albedo coordinate
 };
 
 struct KernelParams {
@@ -145,6 +149,81 @@ CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
   return trilerp<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], fx, fy, fz);
 }
 
+// ---- fused-arithmetic ("exact=0") building blocks -------------------------------------
+// Same algorithm, same RNG draws in the same order; only the floating-point evaluation
+// differs from the reference's: MUFU-based log / reciprocal / rsqrt / sincos instead of
+// the IEEE-rounded library calls, fma-folded coordinate transforms, a+f*(b-a) lerps.
+// Results agree with the exact mode to ~1e-6 relative per operation; parity of this
+// mode is the statistical one.
+CVR_DEV float lerp_fast(float a, float b, float f) { return fmaf(f, b - a, a); }
+CVR_DEV float trilerp_fast(const float (&v)[8], float fx, float fy, float fz) {
+  float x00 = lerp_fast(v[0], v[1], fx), x01 = lerp_fast(v[2], v[3], fx);
+  float x10 = lerp_fast(v[4], v[5], fx), x11 = lerp_fast(v[6], v[7], fx);
+  return lerp_fast(lerp_fast(x00, x01, fy), lerp_fast(x10, x11, fy), fz);
+}
+CVR_DEV float density_at_fast(const MediumParams& m, const TrackInv& I, V3 p) {
+  float cx = fmaf(p.x, I.rx, I.nqrx), cy = fmaf(p.y, I.ry, I.nqry), cz = fmaf(p.z, I.rz, I.nqrz);
+  float flx = floorf(cx), fly = floorf(cy), flz = floorf(cz);
+  int x1 = (int)flx, y1 = (int)fly, z1 = (int)flz;
+  uint32_t kx = min((uint32_t)(x1 + 1), I.nx), ky = min((uint32_t)(y1 + 1), I.ny),
+           kz = min((uint32_t)(z1 + 1), I.nz);
+  uint32_t cell = kx + I.sy * ky + I.sz * kz;
+  float v[8];
+  ldg256(m.dcells + 8 * (size_t)cell, v);
+  return trilerp_fast(v, cx - flx, cy - fly, cz - flz);
+}
+CVR_DEV V3 albedo_cell8_fast(const MediumParams& m, V3 p) {
+  float cx = p.x * (float)(uint32_t)(m.anx - 1), cy = p.y * (float)(uint32_t)(m.any - 1),
+        cz = p.z * (float)(uint32_t)(m.anz - 1);
+  float flx = floorf(cx), fly = floorf(cy), flz = floorf(cz);
+  size_t kx = cell_index((int)flx, m.anx), ky = cell_index((int)fly, m.any), kz = cell_index((int)flz, m.anz);
+  const float4* A = m.acells + 8 * (kx + (size_t)(m.anx + 1) * (ky + (size_t)(m.any + 1) * kz));
+  float4 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = __ldg(A + i);
+  float fx = cx - flx, fy = cy - fly, fz = cz - flz;
+  float r[8], g[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = a[i].x, g[i] = a[i].y, b[i] = a[i].z;
+  return v3(trilerp_fast(r, fx, fy, fz), trilerp_fast(g, fx, fy, fz), trilerp_fast(b, fx, fy, fz));
+}
+CVR_DEV bool box_intersect_fast(const V3& bmin, const V3& bmax, const V3& o, const V3& d, float& dist,
+                                V3& normal, bool& inside) {
+  V3 inv_r = v3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+  V3 tbot = inv_r * (bmin - o);
+  V3 ttop = inv_r * (bmax - o);
+  V3 tmin = v3(fminf(ttop.x, tbot.x), fminf(ttop.y, tbot.y), fminf(ttop.z, tbot.z));
+  V3 tmax = v3(fmaxf(ttop.x, tbot.x), fmaxf(ttop.y, tbot.y), fmaxf(ttop.z, tbot.z));
+  float largest_tmin = fmaxf(fmaxf(tmin.x, tmin.y), fmaxf(tmin.x, tmin.z));
+  float smallest_tmax = fminf(fminf(tmax.x, tmax.y), fminf(tmax.x, tmax.z));
+  dist = (largest_tmin > CVR_EPS) ? largest_tmin : smallest_tmax;
+  if (dist == ttop.x)
+    normal = v3(1, 0, 0);
+  else if (dist == ttop.y)
+    normal = v3(0, 1, 0);
+  else if (dist == ttop.z)
+    normal = v3(0, 0, 1);
+  else if (dist == tbot.x)
+    normal = v3(-1, 0, 0);
+  else if (dist == tbot.y)
+    normal = v3(0, -1, 0);
+  else if (dist == tbot.z)
+    normal = v3(0, 0, -1);
+  inside = dot(normal, d) > 0;
+  return (smallest_tmax > largest_tmin) && (dist > 0);
+}
+CVR_DEV V3 hg_sample_fast(V3 dir, float g, float e1, float e2) {
+  if (fabsf(g) > CVR_EPS) return hg_sample(dir, g, e1, e2);  // anisotropic phase: exact path
+  float cos_theta = 1.0f - 2.0f * e1;
+  float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+  float sp, cp;
+  __sincosf(CVR_TWOPI * e2, &sp, &cp);
+  float inv_norm = rsqrtf(dir.x * dir.x + dir.z * dir.z);
+  V3 v1 = v3(dir.z * inv_norm, 0.0f, -dir.x * inv_norm);
+  V3 v2 = cross(dir, v1);
+  return sin_theta * cp * v1 + sin_theta * sp * v2 + cos_theta * dir;
+}
+
 // ---- regeneration: camera ray for launch-global work item g (A1/A2 prologue) ----
 template <int RNGM, class Rng>
 CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned long long per_tile,
@@ -182,12 +261,14 @@ CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned lo
 }
 
 // ---- intersect (A5) + escape accumulation (A13) ----
-template <bool COUNT, class Rng>
+template <bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
   if (COUNT) ++C.bounces;
   V3 normal = v3(0, 0, 0);
   bool inside;
-  if (!box_intersect(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside)) {
+  const bool hit = FAST ? box_intersect_fast(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside)
+                        : box_intersect(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside);
+  if (!hit) {
     // escaped: throughput * Le, Le == 1 (Medium.h:174-177)
     float rx = R.thr_x * 1.f, ry = R.thr_y * 1.f, rz = R.thr_z * 1.f;
     if (P.per_path) P.per_path[R.path_lo] = make_float4(rx, ry, rz, 1.f);
@@ -212,8 +293,19 @@ CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) 
 }
 
 // ---- one Woodcock step (A6, A7): Utilities.cuh:146-152 ----
-template <int LAYOUT, bool COUNT, class Rng>
+template <int LAYOUT, bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C) {
+  if (FAST && LAYOUT == LAYOUT_CELL8) {
+    float u = R.rng.next();
+    R.t = fmaf(-__logf(fmaxf(u, CVR_EPS)), I.inv_max_sigmat, R.t);
+    V3 p = v3(fmaf(R.t, R.d.x, R.o.x), fmaf(R.t, R.d.y, R.o.y), fmaf(R.t, R.d.z, R.o.z));
+    float dens = density_at_fast(P.med, I, p);
+    if (COUNT) ++C.dens;
+    bool go_on = (R.t <= R.dist);
+    if (go_on) go_on = (dens * I.sig_ratio < R.rng.next());
+    if (!go_on) R.state = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
+    return;
+  }
   float u = R.rng.next();
   R.t += -logf(fmaxf(u, CVR_EPS)) * I.inv_max_sigmat;
   V3 coord = (R.o + (R.t * R.d)) - v3(I.qx, I.qy, I.qz);
@@ -225,39 +317,51 @@ CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rn
 }
 
 // ---- Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) + bounce cap ----
-template <class Rng>
+template <bool FAST = false, class Rng>
 CVR_DEV void do_roulette(const KernelParams& P, PathRegs<Rng>& R) {
   R.state = S_ISECT;
   if (P.rr) {
     float p_survive = fminf(1.f, fmaxf(fmaxf(R.thr_x, R.thr_y), R.thr_z));
     if (R.rng.next() > p_survive) R.state = S_IDLE;
-    R.thr_x = R.thr_x * 1.f / p_survive;
-    R.thr_y = R.thr_y * 1.f / p_survive;
-    R.thr_z = R.thr_z * 1.f / p_survive;
+    if (FAST) {
+      float ip = __fdividef(1.f, p_survive);
+      R.thr_x *= ip, R.thr_y *= ip, R.thr_z *= ip;
+    } else {
+      R.thr_x = R.thr_x * 1.f / p_survive;
+      R.thr_y = R.thr_y * 1.f / p_survive;
+      R.thr_z = R.thr_z * 1.f / p_survive;
+    }
   }
   ++R.bounces;
   if (P.max_bounces && R.bounces >= P.max_bounces) R.state = S_IDLE;
 }
 
 // ---- scatter event (A8, A9): NaiveVolPTsk_kernel.cuh:67-71 / Regeneration...:212-216 ----
-template <int LAYOUT, bool COUNT, class Rng>
+template <int LAYOUT, bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
   if (P.pullback)
     R.o = R.o + R.d * R.t - R.d * CVR_EPS;
   else
     R.o = R.o + R.d * R.t;
-  V3 ac = (R.o - P.med.box_min) / (P.med.box_max - P.med.box_min);
-  V3 albedo = albedo_lookup<LAYOUT>(P.med, ac);
+  V3 albedo;
+  if (FAST && LAYOUT == LAYOUT_CELL8) {
+    V3 ac = v3((R.o.x - P.med.box_min.x) * P.inv.aix, (R.o.y - P.med.box_min.y) * P.inv.aiy,
+               (R.o.z - P.med.box_min.z) * P.inv.aiz);
+    albedo = P.med.albedo_const ? v3(P.med.albedo_r, P.med.albedo_g, P.med.albedo_b) : albedo_cell8_fast(P.med, ac);
+  } else {
+    V3 ac = (R.o - P.med.box_min) / (P.med.box_max - P.med.box_min);
+    albedo = albedo_lookup<LAYOUT>(P.med, ac);
+  }
   if (COUNT) ++C.alb;
   R.thr_x = R.thr_x * albedo.x, R.thr_y = R.thr_y * albedo.y, R.thr_z = R.thr_z * albedo.z;
   float e1 = R.rng.next();
   float e2 = R.rng.next();
-  R.d = hg_sample(R.d, P.med.hg_g, e1, e2);
-  do_roulette(P, R);
+  R.d = FAST ? hg_sample_fast(R.d, P.med.hg_g, e1, e2) : hg_sample(R.d, P.med.hg_g, e1, e2);
+  do_roulette<FAST>(P, R);
 }
 
 // ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
-template <class Rng>
+template <bool FAST = false, class Rng>
 CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
   Frame frame;
   frame.from_z(normal_from_code(R.ncode));
@@ -270,7 +374,7 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
     R.d = frame.to_world(R.d);
     R.o = R.o + R.d * CVR_EPS;
   }
-  do_roulette(P, R);
+  do_roulette<FAST>(P, R);
 }
 
 template <bool COUNT>
@@ -622,7 +726,7 @@ CVR_DEV unsigned q_pop_into(const PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl
   return 0u;
 }
 
-template <int RNGM, int LAYOUT, bool COUNT>
+template <int RNGM, int LAYOUT, bool COUNT, bool FAST>
 __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     k_volpt_queued(const __grid_constant__ KernelParams P) {
   typedef Xorwow Rng;
@@ -699,11 +803,11 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
       if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
       if (exhausted && !was && lane == 0) s_ctl.exhausted = 1;
     } else if (key == 1) {
-      if (have) do_scatter<LAYOUT, COUNT>(P, R, C);
+      if (have) do_scatter<LAYOUT, COUNT, FAST>(P, R, C);
     } else if (key == 2) {
-      if (have) do_boundary(P, R);
+      if (have) do_boundary<FAST>(P, R);
     }
-    if (have && R.state == S_ISECT) do_isect<COUNT>(P, R, C);
+    if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
 
     // ---------------------------------------------------------------- Woodcock steps
     for (int it = 0; it < P.track_steps; ++it) {
@@ -716,7 +820,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
         if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
         if (__shfl_sync(FULL, waiting, 0) != 0u) break;
       }
-      if (have && R.state == S_TRACK) do_track_step<LAYOUT, COUNT>(P, I, R, C);
+      if (have && R.state == S_TRACK) do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
     }
 
     // ---------------------------------------------------------------- write back + push

@@ -51,6 +51,7 @@ struct cvr_renderer {
   int sched = 2;  // 0 = lane-persistent, 1 = block-sorted wavefront, 2 = queued wavefront
   int track_steps = 8;
   int track_min_lanes = 8;
+  int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
 
   // launcher state
   KernelParams P{};
@@ -66,6 +67,8 @@ struct cvr_renderer {
   float* d_dcells = nullptr;
   float4* d_albedo = nullptr;
   float4* d_acells = nullptr;
+  float* d_majorant = nullptr;
+  uint32_t maj_dim[3] = {0, 0, 0};
   unsigned long long* d_head = nullptr;
   DeviceCounters* d_ctr = nullptr;
   bool allocated = false;
@@ -115,7 +118,17 @@ int fail(cvr_handle h, const char* fmt, ...) {
 
 typedef void (*kernel_fn)(const KernelParams);
 
-kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1) {
+kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1, int tracking = 0) {
+  if (tracking == 1) {
+    if (sched != 2 || layout != LAYOUT_CELL8) return nullptr;
+    if (rng_mode == RNG_XORWOW_PATH)
+      return count ? (kernel_fn)k_volpt_queued<RNG_XORWOW_PATH, LAYOUT_CELL8, true, true, true>
+                   : (kernel_fn)k_volpt_queued<RNG_XORWOW_PATH, LAYOUT_CELL8, false, true, true>;
+    if (rng_mode == RNG_XORWOW_THREAD)
+      return count ? (kernel_fn)k_volpt_queued<RNG_XORWOW_THREAD, LAYOUT_CELL8, true, true, true>
+                   : (kernel_fn)k_volpt_queued<RNG_XORWOW_THREAD, LAYOUT_CELL8, false, true, true>;
+    return nullptr;
+  }
 #define CVR_K(R, L)                                      \
   if (sched == 0 && rng_mode == R && layout == L)        \
     return count ? (kernel_fn)k_volpt<R, L, true> : (kernel_fn)k_volpt<R, L, false>;
@@ -157,6 +170,8 @@ void free_volume(cvr_handle h) {
   cudaFree(h->d_dcells);
   cudaFree(h->d_albedo);
   cudaFree(h->d_acells);
+  cudaFree(h->d_majorant);
+  h->d_majorant = nullptr;
   h->d_density = h->d_dcells = nullptr;
   h->d_albedo = h->d_acells = nullptr;
   h->scene_set = false;
@@ -174,7 +189,7 @@ int ensure_allocated(cvr_handle h) {
 
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking);
   if (!k) return fail(h, "no kernel for sched=%d rng=%d layout=%d (philox needs sched=lane)", h->sched, h->rng_mode, h->layout);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
@@ -216,6 +231,11 @@ void fill_track_inv(KernelParams& P) {
   I.aix = 1.0f / ex, I.aiy = 1.0f / ey, I.aiz = 1.0f / ez;
 }
 
+void fill_majorant(cvr_handle h) {
+  h->P.inv.majorant = h->d_majorant;
+  h->P.inv.mx = h->maj_dim[0], h->P.inv.my = h->maj_dim[1], h->P.inv.mz = h->maj_dim[2];
+}
+
 // fills the per-launch part of the kernel parameters and launches
 int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const uint2* origins,
            uint32_t n_launch_tiles, uint32_t tile_first, uint32_t tile_stride, uint32_t seed,
@@ -227,6 +247,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   if (ensure_allocated(h) || ensure_init(h)) return 1;
   KernelParams& P = h->P;
   fill_track_inv(P);
+  fill_majorant(h);
   P.npix = (uint32_t)(P.cam.res_x * P.cam.res_y);  // (uint)(c_resolution.x * c_resolution.y)
   P.tile_w = (uint32_t)P.cam.res_x;
   P.path_begin = path_begin;
@@ -251,7 +272,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking);
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
@@ -390,7 +411,13 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     if (h->scene_set) return fail(h, "layout must be chosen before cvr_set_scene");
     h->inited = false;
   } else if (k == "tracking") {
-    if (v != "global") return fail(h, "tracking=%s is not available in this build (global only)", value);
+    if (v == "global")
+      h->tracking = 0;
+    else if (v == "local")
+      h->tracking = 1;
+    else
+      return fail(h, "tracking: unknown value '%s' (global | local)", value);
+    h->inited = false;
   } else if (k == "exact") {
     h->exact = atoi(value) ? 1 : 0;
     h->inited = false;
@@ -444,7 +471,7 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "layout")
     v = h->layout == LAYOUT_CELL8 ? "cell8" : "linear";
   else if (k == "tracking")
-    v = "global";
+    v = h->tracking ? "local" : "global";
   else if (k == "exact")
     v = std::to_string(h->sched == 2 ? h->exact : 1);
   else if (k == "russian_roulette")
@@ -513,6 +540,15 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     CVR_CUDA(h, cudaMalloc(&h->d_dcells, ncell * 8 * sizeof(float)));
     int g = (int)std::min<size_t>((ncell + bt - 1) / bt, (size_t)h->sm_count * 32);
     k_build_density_cells<<<g, bt, 0, h->stream>>>(h->d_density, m.dnx, m.dny, m.dnz, (float4*)h->d_dcells);
+    CVR_CUDA(h, cudaGetLastError());
+    // majorant bricks for tracking=local
+    h->maj_dim[0] = (uint32_t)(m.dnx + 1 + CVR_BRICK - 1) / CVR_BRICK;
+    h->maj_dim[1] = (uint32_t)(m.dny + 1 + CVR_BRICK - 1) / CVR_BRICK;
+    h->maj_dim[2] = (uint32_t)(m.dnz + 1 + CVR_BRICK - 1) / CVR_BRICK;
+    size_t n_bricks = (size_t)h->maj_dim[0] * h->maj_dim[1] * h->maj_dim[2];
+    CVR_CUDA(h, cudaMalloc(&h->d_majorant, n_bricks * sizeof(float)));
+    k_build_majorant<<<(unsigned)((n_bricks * 32 + bt - 1) / bt), bt, 0, h->stream>>>(
+        (const float4*)h->d_dcells, m.dnx, m.dny, m.dnz, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2], h->d_majorant);
     CVR_CUDA(h, cudaGetLastError());
   }
   m.albedo_const = s->albedo ? 0 : 1;

@@ -37,7 +37,15 @@ struct TrackInv {
   float nqrx, nqry, nqrz;  // -q * r : grid coordinate = fma(p, r, nqr)
   float sig_ratio;         // scale * inv_max_sigmat : accept test = density * sig_ratio < u
   float aix, aiy, aiz;     // 1 / (box_max - box_min) for the albedo coordinate
+  // local-majorant tracking ("tracking=local"): max density per brick of CVR_BRICK^3 cells
+  const float* __restrict__ majorant;
+  uint32_t mx, my, mz;     // brick-grid dims = ceil((n + 1) / CVR_BRICK)
 };
+
+#ifndef CVR_BRICK_LOG2
+#define CVR_BRICK_LOG2 3
+#endif
+#define CVR_BRICK (1 << CVR_BRICK_LOG2)
 
 struct KernelParams {
   CameraParams cam;
@@ -314,6 +322,63 @@ CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rn
   bool go_on = (R.t <= R.dist);
   if (go_on) go_on = (event_density * I.inv_max_sigmat < R.rng.next());
   if (!go_on) R.state = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
+}
+
+// ---- one step of LOCAL-majorant delta tracking ("tracking=local") ----------------------
+// Same unbiased estimator as Woodcock tracking, but the majorant is piecewise constant
+// over bricks of CVR_BRICK^3 lookup cells (the "majorant mip" of the design): inside a
+// brick with majorant mu the free-flight step is drawn with sigma = scale*mu; a step that
+// leaves the brick moves the path to the brick face without a lookup (memoryless
+// restart); bricks with mu == 0 are skipped without a draw.  Fewer null collisions =>
+// fewer lookups per path.  RNG consumption differs from the reference's global-majorant
+// loop, so parity of this mode is statistical.  `texit`/`mu` describe the
+// brick the path is in and are recomputed whenever texit <= t.
+template <bool COUNT, class Rng>
+CVR_DEV void do_track_step_local(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C,
+                                 float& texit, float& mu) {
+  if (texit <= R.t) {
+    // grid-space ray: g(t) = fma(o + t d, r, -q r); brick faces sit at g = CVR_BRICK*j - 1
+    const float gdx = R.d.x * I.rx, gdy = R.d.y * I.ry, gdz = R.d.z * I.rz;
+    const float g0x = fmaf(R.o.x, I.rx, I.nqrx), g0y = fmaf(R.o.y, I.ry, I.nqry), g0z = fmaf(R.o.z, I.rz, I.nqrz);
+    const float tp = R.t + 1e-6f + 1e-6f * fabsf(R.t);  // probe just inside the next brick
+    const float gx = fmaf(tp, gdx, g0x), gy = fmaf(tp, gdy, g0y), gz = fmaf(tp, gdz, g0z);
+    const float inv_b = 1.0f / CVR_BRICK;
+    const float jx = floorf((gx + 1.0f) * inv_b), jy = floorf((gy + 1.0f) * inv_b), jz = floorf((gz + 1.0f) * inv_b);
+    // exit parameter of this brick along the ray
+    const float bx = (gdx > 0.f ? jx + 1.0f : jx) * CVR_BRICK - 1.0f;
+    const float by = (gdy > 0.f ? jy + 1.0f : jy) * CVR_BRICK - 1.0f;
+    const float bz = (gdz > 0.f ? jz + 1.0f : jz) * CVR_BRICK - 1.0f;
+    const float big = 3.0e38f;
+    float ex = gdx != 0.f ? __fdividef(bx - g0x, gdx) : big;
+    float ey = gdy != 0.f ? __fdividef(by - g0y, gdy) : big;
+    float ez = gdz != 0.f ? __fdividef(bz - g0z, gdz) : big;
+    texit = fmaxf(fminf(fminf(ex, ey), ez), tp);  // always makes progress
+    // majorant of the brick that holds the lookup CELL of the probe point (same clamping
+    // as the lookup: out-of-range coordinates use the far-edge cell, Q2)
+    uint32_t kx = min((uint32_t)((int)floorf(gx) + 1), I.nx), ky = min((uint32_t)((int)floorf(gy) + 1), I.ny),
+             kz = min((uint32_t)((int)floorf(gz) + 1), I.nz);
+    uint32_t b = (kx >> CVR_BRICK_LOG2) + I.mx * ((ky >> CVR_BRICK_LOG2) + I.my * (kz >> CVR_BRICK_LOG2));
+    mu = __ldg(I.majorant + b);
+  }
+  const bool last = texit >= R.dist;  // this brick reaches the end of the segment
+  const float tend = last ? R.dist : texit;
+  if (mu <= 0.f) {  // empty brick: skip it
+    R.t = texit;
+    if (last) R.state = S_BOUNDARY;
+    return;
+  }
+  float u = R.rng.next();
+  float tn = fmaf(-__logf(fmaxf(u, CVR_EPS)), __fdividef(1.0f, P.med.scale * mu), R.t);
+  if (tn >= tend) {  // left the brick (or the medium) without a collision
+    R.t = texit;
+    if (last) R.state = S_BOUNDARY;
+    return;
+  }
+  R.t = tn;
+  V3 p = v3(fmaf(R.t, R.d.x, R.o.x), fmaf(R.t, R.d.y, R.o.y), fmaf(R.t, R.d.z, R.o.z));
+  float dens = density_at_fast(P.med, I, p);
+  if (COUNT) ++C.dens;
+  if (dens >= R.rng.next() * mu) R.state = S_SCATTER;  // real collision with probability dens / mu
 }
 
 // ---- Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) + bounce cap ----
@@ -726,7 +791,7 @@ CVR_DEV unsigned q_pop_into(const PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl
   return 0u;
 }
 
-template <int RNGM, int LAYOUT, bool COUNT, bool FAST>
+template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false>
 __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     k_volpt_queued(const __grid_constant__ KernelParams P) {
   typedef Xorwow Rng;
@@ -810,6 +875,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
 
     // ---------------------------------------------------------------- Woodcock steps
+    float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
     for (int it = 0; it < P.track_steps; ++it) {
       unsigned trk = __ballot_sync(FULL, have && R.state == S_TRACK);
       if (trk == 0) break;
@@ -820,7 +886,12 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
         if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
         if (__shfl_sync(FULL, waiting, 0) != 0u) break;
       }
-      if (have && R.state == S_TRACK) do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
+      if (have && R.state == S_TRACK) {
+        if (LOCAL)
+          do_track_step_local<COUNT>(P, I, R, C, texit, mu);
+        else
+          do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
+      }
     }
 
     // ---------------------------------------------------------------- write back + push
@@ -876,6 +947,28 @@ __global__ void k_build_albedo_cells(const float4* __restrict__ A, int nx, int n
     size_t Z = (corner & 4) ? cell_hi(kz, nz) : cell_lo(kz, nz);
     cells[i] = A[X + (size_t)nx * (Y + (size_t)ny * Z)];
   }
+}
+
+// majorant brick grid over the cell8 density layout: max of every corner value of every
+// cell in the brick (so it bounds any trilinear lookup whose cell lies in the brick)
+__global__ void k_build_majorant(const float4* __restrict__ cells, int nx, int ny, int nz, uint32_t mx,
+                                 uint32_t my, uint32_t mz, float* __restrict__ maj) {
+  // one warp per brick, lanes stride over its cells
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  const uint32_t n_bricks = mx * my * mz;
+  if (warp >= n_bricks) return;
+  const uint32_t bx = warp % mx, by = (warp / mx) % my, bz = warp / (mx * my);
+  float m = 0.f;
+  for (uint32_t i = lane; i < CVR_BRICK * CVR_BRICK * CVR_BRICK; i += 32) {
+    uint32_t kx = bx * CVR_BRICK + (i % CVR_BRICK), ky = by * CVR_BRICK + ((i / CVR_BRICK) % CVR_BRICK),
+             kz = bz * CVR_BRICK + i / (CVR_BRICK * CVR_BRICK);
+    if (kx > (uint32_t)nx || ky > (uint32_t)ny || kz > (uint32_t)nz) continue;
+    size_t cell = kx + (size_t)(nx + 1) * (ky + (size_t)(ny + 1) * kz);
+    float4 a = cells[2 * cell], b = cells[2 * cell + 1];
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+  }
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if (lane == 0) maj[warp] = m;
 }
 
 // ---------------------------------------------------------------- resolve (A16)

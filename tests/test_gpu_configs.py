@@ -112,3 +112,39 @@ def test_c3_manix_full_size_tiles(cvr):
     assert np.max(np.abs(a[good] - b[good])) <= 2e-5
     assert np.all(img[1020:] == -3.0)
     kl.close()
+
+
+def test_more_than_2_to_32_paths_in_one_launch(cvr):
+    """Q14: the reference's uint n_paths / int tid overflow beyond 2^32 paths per launch;
+    here the path queue is 64-bit.  4096^2 pixels x 257 spp = 4.31e9 paths, camera looking
+    away from the box so that every path escapes at once: the image must be exactly 1."""
+    sc = cvr.scenes.bucky()
+    res, spp = 4096, 257
+    kl = cvr.RegenerationVolPTsk(0)
+    kl.setScene(sc)
+    img = kl.renderImage((res, res), (1, 1), spp, inv_view=[1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 100.0])
+    c = kl.counters()
+    assert c["paths"] == res * res * spp > 2 ** 32
+    assert c["escaped"] == c["paths"] and c["density_lookups"] == 0
+    assert np.array_equal(img[..., :3], np.ones((res, res, 3), np.float32))
+    kl.close()
+
+
+def test_hbm_resident_volume_runs_and_matches_small_grid_statistics(cvr):
+    """fbm 384^3 with constant albedo 0.99 (C4-like, long multi-scatter paths): the cell8
+    layout is 1.8 GB, far beyond L2, so lookups are HBM-bound; tracking=local must agree
+    with tracking=global statistically."""
+    sc = cvr.scenes.fbm(384)
+    res, spp = 256, 16
+    out = {}
+    for tr in ("global", "local"):
+        kl = cvr.RegenerationVolPTsk(0, tracking=tr)
+        kl.setScene(sc)
+        kl.setSeed(3)
+        img = kl.renderImage((res, res), (1, 1), spp, fov_x=sc.fov_x)[..., :3]
+        out[tr] = (float(np.nanmean(img)), kl.counters())
+        kl.close()
+    (mg, cg), (ml, cl) = out["global"], out["local"]
+    assert abs(mg - ml) / mg <= 0.01
+    assert abs(cg["bounces"] - cl["bounces"]) / cg["bounces"] <= 0.02
+    assert cl["density_lookups"] < cg["density_lookups"]

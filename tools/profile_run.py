@@ -11,7 +11,7 @@ spp = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 opts = dict(a.split("=", 1) for a in sys.argv[5:])
 kernel = opts.pop("kernel", "regenerationSK")
-sc = scenes.make(scene)
+sc = scenes.make(scene.split(':')[0], **({'n': int(scene.split(':')[1])} if ':' in scene else {}))
 kl = createLauncher(kernel, 0, **opts)
 kl.setScene(sc)
 for i in range(reps):

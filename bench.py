@@ -336,6 +336,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "resolution": [RES, RES], "spp_per_gpu": SPP, "total_spp": total_spp,
                    "kernel": "regenerationSK", "rng": kl.getOption("rng"), "layout": kl.getOption("layout"),
+                   "sched": kl.getOption("sched"), "arithmetic": "fused (exact=0)" if kl.getOption("exact") == "0" else "reference order (exact=1)",
+                   "tracking": kl.getOption("tracking"),
                    "sharding": "spp" if world > 1 else "none", "l2": "flushed between steps (256 MiB write)",
                    "image_mean": img_mean, "nan_pixels": nan_px},
         "clocks": clk.summary(),

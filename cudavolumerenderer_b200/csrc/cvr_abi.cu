@@ -52,6 +52,7 @@ struct cvr_renderer {
   int track_steps = 8;
   int track_min_lanes = 8;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
+  int fix_nan = 0;
 
   // launcher state
   KernelParams P{};
@@ -268,6 +269,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.loop_threshold = h->loop_threshold;
   P.track_steps = h->track_steps;
   P.track_min_lanes = h->track_min_lanes;
+  P.fix_nan = h->fix_nan;
   P.rr = h->rr;
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
@@ -453,6 +455,8 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     h->track_steps = t;
   } else if (k == "track_min_lanes") {
     h->track_min_lanes = atoi(value);
+  } else if (k == "fix_nan") {
+    h->fix_nan = atoi(value) ? 1 : 0;
   } else if (k == "counters") {
     h->counters = atoi(value) ? 1 : 0;
     h->inited = false;
@@ -492,6 +496,8 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(h->track_steps);
   else if (k == "track_min_lanes")
     v = std::to_string(h->track_min_lanes);
+  else if (k == "fix_nan")
+    v = std::to_string(h->fix_nan);
   else if (k == "kernel")
     v = h->kernel_name;
   else

@@ -76,6 +76,7 @@ struct KernelParams {
   int rr_after_escape;  // thread-rng regeneration/streaming: the roulette draw is consumed after an escape (Q8)
   int track_steps;      // sorted scheduler: Woodcock steps per round
   int track_min_lanes;  // sorted scheduler: leave the step loop when fewer lanes are still tracking
+  int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
 };
 
 enum : int { S_IDLE = 0, S_ISECT = 1, S_TRACK = 2, S_SCATTER = 3, S_BOUNDARY = 4, S_DONE = 5 };
@@ -279,8 +280,10 @@ CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) 
   if (!hit) {
     // escaped: throughput * Le, Le == 1 (Medium.h:174-177)
     float rx = R.thr_x * 1.f, ry = R.thr_y * 1.f, rz = R.thr_z * 1.f;
+    // the reference lets a NaN throughput through (u == 1.0 in sampleVisible11)
+    const bool keep = !P.fix_nan || (fabsf(rx) <= 3.0e38f && fabsf(ry) <= 3.0e38f && fabsf(rz) <= 3.0e38f);
     if (P.per_path) P.per_path[R.path_lo] = make_float4(rx, ry, rz, 1.f);
-    if (P.out) {
+    if (P.out && keep) {
       float4* px = P.out + R.out_idx;
       atomicAdd(&px->x, rx);
       atomicAdd(&px->y, ry);

@@ -230,6 +230,7 @@ void fill_track_inv(KernelParams& P) {
   I.nqrx = -I.qx * I.rx, I.nqry = -I.qy * I.ry, I.nqrz = -I.qz * I.rz;
   I.sig_ratio = m.scale * I.inv_max_sigmat;
   I.aix = 1.0f / ex, I.aiy = 1.0f / ey, I.aiz = 1.0f / ez;
+  I.neg_ln2_inv_sigmat = -0.69314718055994530942f * I.inv_max_sigmat;
 }
 
 void fill_majorant(cvr_handle h) {

@@ -37,6 +37,7 @@ struct TrackInv {
   float nqrx, nqry, nqrz;  // -q * r : grid coordinate = fma(p, r, nqr)
   float sig_ratio;         // scale * inv_max_sigmat : accept test = density * sig_ratio < u
   float aix, aiy, aiz;     // 1 / (box_max - box_min) for the albedo coordinate
+  float neg_ln2_inv_sigmat;  // -ln(2) * inv_max_sigmat : free-flight step = lg2(u) * this
   // local-majorant tracking ("tracking=local"): max density per brick of CVR_BRICK^3 cells
   const float* __restrict__ majorant;
   uint32_t mx, my, mz;     // brick-grid dims = ceil((n + 1) / CVR_BRICK)
@@ -79,7 +80,10 @@ struct KernelParams {
   int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
 };
 
-enum : int { S_IDLE = 0, S_ISECT = 1, S_TRACK = 2, S_SCATTER = 3, S_BOUNDARY = 4, S_DONE = 5 };
+// S_BOUNDARY_P = boundary event whose FIRST uniform is already drawn and parked in
+// PathRegs::t (the fast tracking loop draws both uniforms of a Woodcock step up front; the
+// reference does not consume the second one when the step left the medium).
+enum : int { S_IDLE = 0, S_ISECT = 1, S_TRACK = 2, S_SCATTER = 3, S_BOUNDARY = 4, S_DONE = 5, S_BOUNDARY_P = 6 };
 
 CVR_DEV V3 normal_from_code(int c) {
   // 0:+x 1:+y 2:+z 3:-x 4:-y 5:-z
@@ -134,7 +138,7 @@ struct PathRegs {
 };
 
 struct LaneCounters {
-  uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0;
+  uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0, spec = 0;
 };
 
 // Loop invariants of the Woodcock step (the reference recomputes them every
@@ -155,7 +159,7 @@ CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
   uint32_t cell = kx + I.sy * ky + I.sz * kz;
   float v[8];
   ldg256(m.dcells + 8 * (size_t)cell, v);
-  return trilerp<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], fx, fy, fz);
+  return trilerp<true>(v[0], v[2], v[4], v[6], v[1], v[3], v[5], v[7], fx, fy, fz);
 }
 
 // ---- fused-arithmetic ("exact=0") building blocks -------------------------------------
@@ -165,21 +169,73 @@ CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
 // Results agree with the exact mode to ~1e-6 relative per operation; parity of this
 // mode is the statistical one.
 CVR_DEV float lerp_fast(float a, float b, float f) { return fmaf(f, b - a, a); }
+#ifndef CVR_TRILERP_X2
+#define CVR_TRILERP_X2 1
+#endif
+// Blackwell packed fp32 arithmetic (PTX add/sub/fma .f32x2 -> SASS FADD2 / FFMA2): one
+// instruction blends two corner pairs.
+typedef unsigned long long f32x2_t;
+CVR_DEV f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+CVR_DEV void unpack2(f32x2_t r, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+CVR_DEV f32x2_t lerp2(f32x2_t a, f32x2_t b, f32x2_t f) {  // a + f * (b - a), both halves
+  f32x2_t d, r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f), "l"(d), "l"(a));
+  return r;
+}
+// v in the cell8 corner order (cvr_device.cuh): pairs (v0,v1)=(x1,y1,z1|z2), (v2,v3)=(x2,y1),
+// (v4,v5)=(x1,y2), (v6,v7)=(x2,y2): x blend, y blend on pairs, z blend scalar = 8 instructions
 CVR_DEV float trilerp_fast(const float (&v)[8], float fx, float fy, float fz) {
-  float x00 = lerp_fast(v[0], v[1], fx), x01 = lerp_fast(v[2], v[3], fx);
-  float x10 = lerp_fast(v[4], v[5], fx), x11 = lerp_fast(v[6], v[7], fx);
-  return lerp_fast(lerp_fast(x00, x01, fy), lerp_fast(x10, x11, fy), fz);
+#if CVR_TRILERP_X2
+  const f32x2_t FX = pack2(fx, fx), FY = pack2(fy, fy);
+  f32x2_t R = lerp2(pack2(v[0], v[1]), pack2(v[2], v[3]), FX);
+  f32x2_t S = lerp2(pack2(v[4], v[5]), pack2(v[6], v[7]), FX);
+  float t0, t1;
+  unpack2(lerp2(R, S, FY), t0, t1);
+  return lerp_fast(t0, t1, fz);
+#else
+  float r0 = lerp_fast(v[0], v[2], fx), r1 = lerp_fast(v[1], v[3], fx);
+  float s0 = lerp_fast(v[4], v[6], fx), s1 = lerp_fast(v[5], v[7], fx);
+  return lerp_fast(lerp_fast(r0, s0, fy), lerp_fast(r1, s1, fy), fz);
+#endif
+}
+// floor() without the conversion pipe: x + 1.5*2^23 rounded toward -inf is floor(x) + 1.5*2^23
+// exactly for |x| < 2^22, so the integer is in the low mantissa bits and the float floor is
+// one exact subtraction away (FADD.RM + FADD instead of F2I.FLOOR + FRND.FLOOR).
+#define CVR_FLOOR_MAGIC 12582912.0f
+#define CVR_FLOOR_MAGIC_BITS 0x4B400000
+// A lookup split into "address + issue the 256-bit load" and "blend", so that a caller can
+// put several loads in flight before the first blend.
+struct CellFetch {
+  float v[8];
+  float fx, fy, fz;
+};
+CVR_DEV void cell_fetch(const MediumParams& m, const TrackInv& I, float cx, float cy, float cz, CellFetch& F) {
+  const float bx = __fadd_rd(cx, CVR_FLOOR_MAGIC), by = __fadd_rd(cy, CVR_FLOOR_MAGIC), bz = __fadd_rd(cz, CVR_FLOOR_MAGIC);
+  // cell index k = x1 + 1, clamped like the reference's fetches (Q2: negative x1 wraps to the far edge)
+  uint32_t kx = min((uint32_t)(__float_as_int(bx) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nx),
+           ky = min((uint32_t)(__float_as_int(by) - (CVR_FLOOR_MAGIC_BITS - 1)), I.ny),
+           kz = min((uint32_t)(__float_as_int(bz) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nz);
+  uint32_t cell = kx + I.sy * ky + I.sz * kz;
+  ldg256(m.dcells + 8 * (size_t)cell, F.v);
+  F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
+}
+CVR_DEV float density_at_grid(const MediumParams& m, const TrackInv& I, float cx, float cy, float cz) {
+  CellFetch F;
+  cell_fetch(m, I, cx, cy, cz, F);
+  return trilerp_fast(F.v, F.fx, F.fy, F.fz);
 }
 CVR_DEV float density_at_fast(const MediumParams& m, const TrackInv& I, V3 p) {
-  float cx = fmaf(p.x, I.rx, I.nqrx), cy = fmaf(p.y, I.ry, I.nqry), cz = fmaf(p.z, I.rz, I.nqrz);
-  float flx = floorf(cx), fly = floorf(cy), flz = floorf(cz);
-  int x1 = (int)flx, y1 = (int)fly, z1 = (int)flz;
-  uint32_t kx = min((uint32_t)(x1 + 1), I.nx), ky = min((uint32_t)(y1 + 1), I.ny),
-           kz = min((uint32_t)(z1 + 1), I.nz);
-  uint32_t cell = kx + I.sy * ky + I.sz * kz;
-  float v[8];
-  ldg256(m.dcells + 8 * (size_t)cell, v);
-  return trilerp_fast(v, cx - flx, cy - fly, cz - flz);
+  return density_at_grid(m, I, fmaf(p.x, I.rx, I.nqrx), fmaf(p.y, I.ry, I.nqry), fmaf(p.z, I.rz, I.nqrz));
+}
+CVR_DEV float lg2_fast(float x) {  // x >= 1e-5 here: no denormal fix-up needed
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 CVR_DEV V3 albedo_cell8_fast(const MediumParams& m, V3 p) {
   float cx = p.x * (float)(uint32_t)(m.anx - 1), cy = p.y * (float)(uint32_t)(m.any - 1),
@@ -191,10 +247,30 @@ CVR_DEV V3 albedo_cell8_fast(const MediumParams& m, V3 p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = __ldg(A + i);
   float fx = cx - flx, fy = cy - fly, fz = cz - flz;
-  float r[8], g[8], b[8];
+#if CVR_TRILERP_X2
+  // corners a[zyx]; each float4 is two aligned pairs (r,g) and (b,w)
+  const f32x2_t FX = pack2(fx, fx), FY = pack2(fy, fy), FZ = pack2(fz, fz);
+  f32x2_t rg[4], bw[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = a[i].x, g[i] = a[i].y, b[i] = a[i].z;
+  for (int i = 0; i < 4; ++i) {
+    rg[i] = lerp2(pack2(a[2 * i].x, a[2 * i].y), pack2(a[2 * i + 1].x, a[2 * i + 1].y), FX);
+    bw[i] = lerp2(pack2(a[2 * i].z, a[2 * i].w), pack2(a[2 * i + 1].z, a[2 * i + 1].w), FX);
+  }
+  f32x2_t rg0 = lerp2(rg[0], rg[1], FY), rg1 = lerp2(rg[2], rg[3], FY);
+  f32x2_t bw0 = lerp2(bw[0], bw[1], FY), bw1 = lerp2(bw[2], bw[3], FY);
+  V3 out;
+  float w;
+  unpack2(lerp2(rg0, rg1, FZ), out.x, out.y);
+  unpack2(lerp2(bw0, bw1, FZ), out.z, w);
+  return out;
+#else
+  float r[8], g[8], b[8];
+  // trilerp_fast expects the density corner order (z fastest inside a pair)
+  const int perm[8] = {0, 4, 1, 5, 2, 6, 3, 7};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = a[perm[i]].x, g[i] = a[perm[i]].y, b[i] = a[perm[i]].z;
   return v3(trilerp_fast(r, fx, fy, fz), trilerp_fast(g, fx, fy, fz), trilerp_fast(b, fx, fy, fz));
+#endif
 }
 CVR_DEV bool box_intersect_fast(const V3& bmin, const V3& bmax, const V3& o, const V3& d, float& dist,
                                 V3& normal, bool& inside) {
@@ -308,7 +384,7 @@ template <int LAYOUT, bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C) {
   if (FAST && LAYOUT == LAYOUT_CELL8) {
     float u = R.rng.next();
-    R.t = fmaf(-__logf(fmaxf(u, CVR_EPS)), I.inv_max_sigmat, R.t);
+    R.t = fmaf(lg2_fast(fmaxf(u, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
     V3 p = v3(fmaf(R.t, R.d.x, R.o.x), fmaf(R.t, R.d.y, R.o.y), fmaf(R.t, R.d.z, R.o.z));
     float dens = density_at_fast(P.med, I, p);
     if (COUNT) ++C.dens;
@@ -325,6 +401,93 @@ CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rn
   bool go_on = (R.t <= R.dist);
   if (go_on) go_on = (event_density * I.inv_max_sigmat < R.rng.next());
   if (!go_on) R.state = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
+}
+
+// ---- the Woodcock step of the fast queued kernel -----------------------------------------
+// Same draws in the same order as do_track_step, restructured for issue slots:
+//  * the ray is carried in GRID space (g0 + t*gd, set up once per batch), so a step needs 3
+//    FFMA for the lookup coordinate instead of 6 and no constant-bank operands;
+//  * both uniforms of the step are drawn up front (straight-line code, no divergent branch
+//    around the second XORWOW update).  The reference does not consume the second uniform
+//    when the step left the medium (Utilities.cuh:148-152: the && short-circuits); in that
+//    case it is PARKED in R.t for the boundary event that follows (state S_BOUNDARY_P), which
+//    takes it as its first draw -- the path sees exactly the reference's sequence.
+struct GridRay {
+  float g0x, g0y, g0z, gdx, gdy, gdz;
+};
+CVR_DEV GridRay grid_ray(const TrackInv& I, const V3& o, const V3& d) {
+  GridRay G;
+  G.g0x = fmaf(o.x, I.rx, I.nqrx), G.g0y = fmaf(o.y, I.ry, I.nqry), G.g0z = fmaf(o.z, I.rz, I.nqrz);
+  G.gdx = d.x * I.rx, G.gdy = d.y * I.ry, G.gdz = d.z * I.rz;
+  // opaque to the optimiser: otherwise ptxas keeps o/d live and re-derives these six values
+  // inside the loop (6 extra instructions + constant loads per step)
+  asm volatile("" : "+f"(G.g0x), "+f"(G.g0y), "+f"(G.g0z), "+f"(G.gdx), "+f"(G.gdy), "+f"(G.gdz));
+  return G;
+}
+template <bool COUNT>
+CVR_DEV void track_step_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
+                             LaneCounters& C) {
+  const float u = R.rng.next();
+  const float u2 = R.rng.next();
+  R.t = fmaf(lg2_fast(fmaxf(u, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
+  const float dens = density_at_grid(P.med, I, fmaf(R.t, G.gdx, G.g0x), fmaf(R.t, G.gdy, G.g0y),
+                                     fmaf(R.t, G.gdz, G.g0z));
+  if (COUNT) ++C.dens;
+  // select form (no divergent branch): inside ? (accepted ? event : keep tracking) : parked boundary
+  const bool inside = R.t <= R.dist;
+  const bool accepted = !(dens * I.sig_ratio < u2);
+  const int ev = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
+  R.state = inside ? (accepted ? ev : S_TRACK) : S_BOUNDARY_P;
+  R.t = inside ? R.t : u2;
+}
+
+// Two Woodcock steps at once, the second one SPECULATIVE: the position of step 2 depends
+// only on the uniforms (not on the density of step 1), so both 256-bit cell loads are
+// issued back to back and a lane has two L2 round trips in flight (the loop is bound by
+// the load latency of a dependent chain, not by issue slots -- DESIGN.md 3.1).  If step 1
+// ended the segment (collision or exit) the second step never happened: its lookup is
+// counted as speculative and the generator is rolled back by two draws.  The state after 2
+// draws (v2,v3,v4,n1,n2) shares three words with the state after 4 (v4,n1,n2,n3,n4), so
+// the roll-back is six selects on two saved words, not an inverse computation.
+template <bool COUNT>
+CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
+                             LaneCounters& C) {
+  Xorwow& g = R.rng;
+  const uint32_t s2 = g.v2, s3 = g.v3;
+  const float u1 = g.next(), w1 = g.next(), u2 = g.next(), w2 = g.next();
+  const float t1 = fmaf(lg2_fast(fmaxf(u1, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
+  const float t2 = fmaf(lg2_fast(fmaxf(u2, CVR_EPS)), I.neg_ln2_inv_sigmat, t1);
+  CellFetch F1, F2;
+  cell_fetch(P.med, I, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y), fmaf(t1, G.gdz, G.g0z), F1);
+  cell_fetch(P.med, I, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y), fmaf(t2, G.gdz, G.g0z), F2);
+  // both loads must be in flight before the first blend: tie the two results together so
+  // that ptxas cannot consume load 1 (and reuse its registers) before load 2 is issued
+  // (a REAL data dependency: an empty asm leaves nothing for ptxas to order; density values
+  // are finite, so 0 * v is exactly 0 and the blend of step 1 is unchanged)
+  F1.v[0] = __fmaf_rn(0.0f, F2.v[7], F1.v[0]);
+  F1.v[4] = __fmaf_rn(0.0f, F2.v[7], F1.v[4]);
+  const float dens1 = trilerp_fast(F1.v, F1.fx, F1.fy, F1.fz);
+  const float dens2 = trilerp_fast(F2.v, F2.fx, F2.fy, F2.fz);
+  const bool in1 = t1 <= R.dist, in2 = t2 <= R.dist;
+  const bool acc1 = !(dens1 * I.sig_ratio < w1), acc2 = !(dens2 * I.sig_ratio < w2);
+  const bool cont1 = in1 && !acc1;  // step 1 was a null collision inside the medium
+  // the step that decides this lane's fate
+  const float td = cont1 ? t2 : t1, wd = cont1 ? w2 : w1;
+  const bool ind = cont1 ? in2 : in1, accd = cont1 ? acc2 : acc1;
+  const int ev = (td < R.dist) ? S_SCATTER : S_BOUNDARY;
+  R.state = ind ? (accd ? ev : S_TRACK) : S_BOUNDARY_P;
+  R.t = ind ? td : wd;
+  // roll the generator back by two draws when step 2 never happened
+  g.v4 = cont1 ? g.v4 : g.v2;
+  g.v3 = cont1 ? g.v3 : g.v1;
+  g.v2 = cont1 ? g.v2 : g.v0;
+  g.v1 = cont1 ? g.v1 : s3;
+  g.v0 = cont1 ? g.v0 : s2;
+  g.d = cont1 ? g.d : g.d - 2u * 362437u;
+  if (COUNT) {
+    C.dens += cont1 ? 2u : 1u;
+    C.spec += cont1 ? 0u : 1u;
+  }
 }
 
 // ---- one step of LOCAL-majorant delta tracking ("tracking=local") ----------------------
@@ -385,12 +548,12 @@ CVR_DEV void do_track_step_local(const KernelParams& P, const TrackInv& I, PathR
 }
 
 // ---- Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) + bounce cap ----
-template <bool FAST = false, class Rng>
-CVR_DEV void do_roulette(const KernelParams& P, PathRegs<Rng>& R) {
+template <bool FAST = false, class Rng, class Draw>
+CVR_DEV void do_roulette(const KernelParams& P, PathRegs<Rng>& R, Draw& rng) {
   R.state = S_ISECT;
   if (P.rr) {
     float p_survive = fminf(1.f, fmaxf(fmaxf(R.thr_x, R.thr_y), R.thr_z));
-    if (R.rng.next() > p_survive) R.state = S_IDLE;
+    if (rng.next() > p_survive) R.state = S_IDLE;
     if (FAST) {
       float ip = __fdividef(1.f, p_survive);
       R.thr_x *= ip, R.thr_y *= ip, R.thr_z *= ip;
@@ -425,7 +588,7 @@ CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C
   float e1 = R.rng.next();
   float e2 = R.rng.next();
   R.d = FAST ? hg_sample_fast(R.d, P.med.hg_g, e1, e2) : hg_sample(R.d, P.med.hg_g, e1, e2);
-  do_roulette<FAST>(P, R);
+  do_roulette<FAST>(P, R, R.rng);
 }
 
 // ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
@@ -436,13 +599,17 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
   V3 dir = frame.to_local(normalize(v3(-R.d.x, -R.d.y, -R.d.z)));
   R.o = R.o + R.d * R.dist;
   float weight = 1;
+  // S_BOUNDARY_P: the first uniform of this event was drawn by the tracking loop (parked in t)
+  StashRng<Rng> rng{R.rng, R.t, R.state == S_BOUNDARY_P};
   // the sampler writes the LOCAL direction into the ray even when it then fails
-  if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, R.rng, R.d, weight)) {
+  if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
     R.thr_x *= weight, R.thr_y *= weight, R.thr_z *= weight;
     R.d = frame.to_world(R.d);
     R.o = R.o + R.d * CVR_EPS;
   }
-  do_roulette<FAST>(P, R);
+  do_roulette<FAST>(P, R, rng);
+  // nobody drew (grazing hit with roulette off): give the parked uniform back to the stream
+  if (rng.has) R.rng.undo();
 }
 
 template <bool COUNT>
@@ -455,6 +622,7 @@ CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lan
     C.dens += __shfl_xor_sync(FULL, C.dens, s);
     C.alb += __shfl_xor_sync(FULL, C.alb, s);
     C.esc += __shfl_xor_sync(FULL, C.esc, s);
+    C.spec += __shfl_xor_sync(FULL, C.spec, s);
   }
   if (lane == 0) {  // one atomic per warp per counter
     atomicAdd(&P.ctr->paths, (unsigned long long)C.paths);
@@ -462,6 +630,7 @@ CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lan
     atomicAdd(&P.ctr->density_lookups, (unsigned long long)C.dens);
     atomicAdd(&P.ctr->albedo_lookups, (unsigned long long)C.alb);
     atomicAdd(&P.ctr->escaped, (unsigned long long)C.esc);
+    if (C.spec) atomicAdd(&P.ctr->speculative, (unsigned long long)C.spec);
   }
 }
 
@@ -584,9 +753,37 @@ CVR_DEV void slot_load(const PathSlot& s, PathRegs<Xorwow>& R) {
   R.rng.v4 = f.x, R.rng.d = f.y, R.out_idx = f.z, R.path_lo = f.w;
 }
 
+// The tracking loop only changes t, the state and the generator; everything else is
+// written once after the event ("static" part) so that o, d, throughput and the output
+// index are dead registers inside the loop, and a pure tracking batch moves 56 + 32 bytes
+// per path through shared memory instead of 80 + 80.
+CVR_DEV void slot_load_track(const PathSlot& s, PathRegs<Xorwow>& R) {
+  float4 a = s.q0, b = s.q1;
+  uint32_t meta = __float_as_uint(s.q2.w);
+  uint4 e = s.q3;
+  uint2 f = *reinterpret_cast<const uint2*>(&s.q4);
+  R.o = v3(a.x, a.y, a.z), R.t = a.w;
+  R.d = v3(b.x, b.y, b.z), R.dist = b.w;
+  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
+  R.rng.v0 = e.x, R.rng.v1 = e.y, R.rng.v2 = e.z, R.rng.v3 = e.w;
+  R.rng.v4 = f.x, R.rng.d = f.y;
+}
+CVR_DEV void slot_store_static(PathSlot& s, const PathRegs<Xorwow>& R) {
+  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.t);
+  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, R.dist);
+  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, 0.f);
+  reinterpret_cast<uint2*>(&s.q4)[1] = make_uint2(R.out_idx, R.path_lo);
+}
+CVR_DEV void slot_store_dynamic(PathSlot& s, float t, uint32_t meta, const Xorwow& g) {
+  s.q0.w = t;
+  s.q2.w = __uint_as_float(meta);
+  s.q3 = make_uint4(g.v0, g.v1, g.v2, g.v3);
+  reinterpret_cast<uint2*>(&s.q4)[0] = make_uint2(g.v4, g.d);
+}
+
 CVR_DEV int sort_key(int state) {
   // TRACK 0, SCATTER 1, BOUNDARY 2, IDLE 3, DONE 4
-  return state == S_TRACK ? 0 : state == S_SCATTER ? 1 : state == S_BOUNDARY ? 2 : state == S_IDLE ? 3 : 4;
+  return state == S_TRACK ? 0 : state == S_SCATTER ? 1 : (state == S_BOUNDARY || state == S_BOUNDARY_P) ? 2 : state == S_IDLE ? 3 : 4;
 }
 
 template <int RNGM, int LAYOUT, bool COUNT>
@@ -705,6 +902,12 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 #ifndef CVR_QSLOTS
 #define CVR_QSLOTS 512
 #endif
+#ifndef CVR_PAIR
+#define CVR_PAIR 1  // fast tracking loop: two Woodcock steps per iteration, second one speculative
+#endif
+#ifndef CVR_VOTE_EVERY
+#define CVR_VOTE_EVERY 1  // Woodcock steps between two warp votes of the fast tracking loop
+#endif
 
 struct QueueCtl {
   unsigned int head[4];  // pop cursor
@@ -720,12 +923,10 @@ CVR_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *(const vol
 // its new state (warp-aggregated reserve -> write -> ordered commit); finished slots
 // (S_DONE) are only counted.  Must be called by all 32 lanes.
 template <unsigned N>
-CVR_DEV void q_retire(PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl& ctl, bool in_mask, unsigned slot,
-                      const PathRegs<Xorwow>& R, unsigned lane) {
+CVR_DEV void q_retire(uint16_t (*s_q)[N], QueueCtl& ctl, bool in_mask, unsigned slot, int state, unsigned lane) {
   const unsigned FULL = 0xffffffffu;
   const unsigned lane_lt = (1u << lane) - 1u;
-  if (in_mask) slot_store(s_slot[slot], R);
-  const int nk = in_mask ? sort_key(R.state) : 5;
+  const int nk = in_mask ? sort_key(state) : 5;
   unsigned my_p = 0, commit_mask = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -786,7 +987,10 @@ CVR_DEV unsigned q_pop_into(const PathSlot* s_slot, uint16_t (*s_q)[N], QueueCtl
       __threadfence_block();
       if (take) {
         slot = cand;
-        slot_load(s_slot[slot], R);
+        if (key == 0)
+          slot_load_track(s_slot[slot], R);
+        else
+          slot_load(s_slot[slot], R);
       }
       return __ballot_sync(FULL, take);
     }
@@ -876,29 +1080,62 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
       if (have) do_boundary<FAST>(P, R);
     }
     if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
+    // everything the tracking loop does not touch goes back to the slot now
+    if (key != 0 && have) slot_store_static(s_slot[slot], R);
+    const uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
 
     // ---------------------------------------------------------------- Woodcock steps
-    float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
-    for (int it = 0; it < P.track_steps; ++it) {
-      unsigned trk = __ballot_sync(FULL, have && R.state == S_TRACK);
-      if (trk == 0) break;
-      if (it > 0 && __popc(trk) < P.track_min_lanes) {
-        // few lanes left: requeue them so they merge into a full batch -- unless
-        // nobody else is queued for tracking
-        unsigned waiting = 0;
-        if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
-        if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+    if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
+      const GridRay G = grid_ray(I, R.o, R.d);
+#if CVR_PAIR
+      for (int it = 0; it < P.track_steps; it += 2) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
+        if (trk == 0) break;
+        if (it > 0 && __popc(trk) < P.track_min_lanes) {
+          unsigned waiting = 0;
+          if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
+          if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+        }
+        if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
       }
-      if (have && R.state == S_TRACK) {
-        if (LOCAL)
-          do_track_step_local<COUNT>(P, I, R, C, texit, mu);
-        else
-          do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
+#else
+      for (int it = 0; it < P.track_steps; it += CVR_VOTE_EVERY) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
+        if (trk == 0) break;
+        if (it > 0 && __popc(trk) < P.track_min_lanes) {
+          unsigned waiting = 0;
+          if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
+          if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+        }
+#pragma unroll
+        for (int s = 0; s < CVR_VOTE_EVERY; ++s)
+          if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
+      }
+#endif
+    } else {
+      float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
+      for (int it = 0; it < P.track_steps; ++it) {
+        unsigned trk = __ballot_sync(FULL, have && R.state == S_TRACK);
+        if (trk == 0) break;
+        if (it > 0 && __popc(trk) < P.track_min_lanes) {
+          // few lanes left: requeue them so they merge into a full batch -- unless
+          // nobody else is queued for tracking
+          unsigned waiting = 0;
+          if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
+          if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+        }
+        if (have && R.state == S_TRACK) {
+          if (LOCAL)
+            do_track_step_local<COUNT>(P, I, R, C, texit, mu);
+          else
+            do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
+        }
       }
     }
 
     // ---------------------------------------------------------------- write back + push
-    q_retire<N>(s_slot, s_q, s_ctl, have, slot, R, lane);
+    if (have) slot_store_dynamic(s_slot[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
+    q_retire<N>(s_q, s_ctl, have, slot, R.state, lane);
   }
   flush_counters<COUNT>(P, C, lane);
 }
@@ -923,10 +1160,11 @@ __global__ void k_build_density_cells(const float* __restrict__ D, int nx, int n
     size_t Z1 = cell_lo(kz, nz), Z2 = cell_hi(kz, nz);
     size_t sx = (size_t)nx, sxy = (size_t)nx * ny;
     float4 a, b;
-    a.x = D[X1 + sx * Y1 + sxy * Z1], a.y = D[X2 + sx * Y1 + sxy * Z1];
-    a.z = D[X1 + sx * Y2 + sxy * Z1], a.w = D[X2 + sx * Y2 + sxy * Z1];
-    b.x = D[X1 + sx * Y1 + sxy * Z2], b.y = D[X2 + sx * Y1 + sxy * Z2];
-    b.z = D[X1 + sx * Y2 + sxy * Z2], b.w = D[X2 + sx * Y2 + sxy * Z2];
+    // corner order of cvr_device.cuh: (x1,y1,z1) (x1,y1,z2) (x2,y1,z1) (x2,y1,z2) | same for y2
+    a.x = D[X1 + sx * Y1 + sxy * Z1], a.y = D[X1 + sx * Y1 + sxy * Z2];
+    a.z = D[X2 + sx * Y1 + sxy * Z1], a.w = D[X2 + sx * Y1 + sxy * Z2];
+    b.x = D[X1 + sx * Y2 + sxy * Z1], b.y = D[X1 + sx * Y2 + sxy * Z2];
+    b.z = D[X2 + sx * Y2 + sxy * Z1], b.w = D[X2 + sx * Y2 + sxy * Z2];
     cells[2 * i] = a;
     cells[2 * i + 1] = b;
   }
@@ -1025,7 +1263,11 @@ __global__ void k_rng_kat(const int32_t* seeds, int n_seeds, int n, uint32_t* wo
   a.init(seeds[i]);
   b.init(seeds[i]);
   for (int k = 0; k < n; ++k) {
-    words[(size_t)i * n + k] = a.next_u32();
+    // draw, give the draw back, draw again: also pins Xorwow::undo against cuRAND's words
+    uint32_t w0 = a.next_u32();
+    a.undo();
+    uint32_t w1 = a.next_u32();
+    words[(size_t)i * n + k] = (w0 == w1) ? w1 : ~w1;
     uni[(size_t)i * n + k] = b.next();
   }
 }

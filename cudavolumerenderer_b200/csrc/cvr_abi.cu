@@ -48,7 +48,13 @@ struct cvr_renderer {
   int blocks_per_sm = 0;  // 0 = occupancy query
   int loop_threshold = 16;
   int counters = 1;
-  int sched = 2;  // 0 = lane-persistent, 1 = block-sorted wavefront, 2 = queued wavefront
+  int sched = 3;  // 0 = lane-persistent, 1 = block-sorted wavefront, 2 = queued wavefront, 3 = warp-private wavefront
+  int policy = 0; // warp scheduler batch choice (KernelParams::policy)
+  int refill = 0; // warp scheduler: in-place refill period of the tracking loop in steps (0 = off)
+  size_t smem_bytes = 0;  // dynamic shared memory of the selected kernel
+  int warp_slots = 0;     // warp scheduler: path slots per warp (64 | 96), 0 = auto
+  size_t volume_bytes = 0;  // device footprint of the density + albedo lookup layouts
+  int l2_bytes = 0;
   int track_steps = 8;
   int track_min_lanes = 8;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
@@ -119,7 +125,35 @@ int fail(cvr_handle h, const char* fmt, ...) {
 
 typedef void (*kernel_fn)(const KernelParams);
 
-kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1, int tracking = 0) {
+template <int W>
+kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int tracking) {
+  if (tracking == 1) {
+    if (layout != LAYOUT_CELL8) return nullptr;
+    if (rng_mode == RNG_XORWOW_PATH)
+      return count ? (kernel_fn)k_volpt_warp<RNG_XORWOW_PATH, LAYOUT_CELL8, true, true, true, W>
+                   : (kernel_fn)k_volpt_warp<RNG_XORWOW_PATH, LAYOUT_CELL8, false, true, true, W>;
+    if (rng_mode == RNG_XORWOW_THREAD)
+      return count ? (kernel_fn)k_volpt_warp<RNG_XORWOW_THREAD, LAYOUT_CELL8, true, true, true, W>
+                   : (kernel_fn)k_volpt_warp<RNG_XORWOW_THREAD, LAYOUT_CELL8, false, true, true, W>;
+    return nullptr;
+  }
+#define CVR_K(R, L)                                                                                    \
+  if (rng_mode == R && layout == L) {                                                                  \
+    if (exact) return count ? (kernel_fn)k_volpt_warp<R, L, true, false, false, W> : (kernel_fn)k_volpt_warp<R, L, false, false, false, W>; \
+    return count ? (kernel_fn)k_volpt_warp<R, L, true, true, false, W> : (kernel_fn)k_volpt_warp<R, L, false, true, false, W>;           \
+  }
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_PATH, LAYOUT_LINEAR)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
+  CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
+#undef CVR_K
+  return nullptr;
+}
+
+kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1, int tracking = 0, int wslots = 64) {
+  if (sched == 3)
+    return wslots == 96 ? pick_warp_kernel<96>(rng_mode, layout, count, exact, tracking)
+                        : pick_warp_kernel<64>(rng_mode, layout, count, exact, tracking);
   if (tracking == 1) {
     if (sched != 2 || layout != LAYOUT_CELL8) return nullptr;
     if (rng_mode == RNG_XORWOW_PATH)
@@ -188,15 +222,27 @@ int ensure_allocated(cvr_handle h) {
   return 0;
 }
 
+// slots per warp of the warp-private scheduler: "auto" = 96 while the density lookup layout
+// (the stream with ~90 % of the lookups) fits the L2 (fuller batches win), 64 beyond (the L1
+// left next to the slots wins); measurements in cvr_kernels.cuh
+int effective_wslots(cvr_handle h) {
+  if (h->warp_slots) return h->warp_slots;
+  return (h->volume_bytes && h->volume_bytes <= (size_t)h->l2_bytes) ? 96 : 64;
+}
+
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
   if (!k) return fail(h, "no kernel for sched=%d rng=%d layout=%d (philox needs sched=lane)", h->sched, h->rng_mode, h->layout);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
+  // the warp-private scheduler keeps its path slots in DYNAMIC shared memory (may exceed 48 KB)
+  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(h->block, effective_wslots(h)) : 0;
+  if (h->smem_bytes)
+    CVR_CUDA(h, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int per_sm = 0;
-  CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, h->block, 0));
+  CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, h->block, h->smem_bytes));
   if (per_sm < 1) return fail(h, "kernel does not fit an SM at block size %d", h->block);
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < per_sm) per_sm = h->blocks_per_sm;
   h->grid = per_sm * h->sm_count;
@@ -271,16 +317,18 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.track_steps = h->track_steps;
   P.track_min_lanes = h->track_min_lanes;
   P.fix_nan = h->fix_nan;
+  P.policy = h->policy;
+  P.refill = h->refill;
   P.rr = h->rr;
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
   CVR_CUDA(h, cudaEventRecord(e0, h->stream));
-  k<<<h->grid, h->block, 0, h->stream>>>(P);
+  k<<<h->grid, h->block, h->smem_bytes, h->stream>>>(P);
   CVR_CUDA(h, cudaGetLastError());
   CVR_CUDA(h, cudaEventRecord(e1, h->stream));
   h->timing.emplace_back(e0, e1);
@@ -345,6 +393,7 @@ int cvr_create(const char* kernel_name, int device, cvr_handle* out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   h->sm_count = prop.multiProcessorCount;
+  h->l2_bytes = prop.l2CacheSize;
   if (prop.major < 10) {
     fail(nullptr, "cvr_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
          prop.major, prop.minor);
@@ -447,8 +496,23 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
       h->sched = 1;
     else if (v == "queued")
       h->sched = 2;
+    else if (v == "warp")
+      h->sched = 3;
     else
-      return fail(h, "sched: unknown value '%s' (lane | sorted | queued)", value);
+      return fail(h, "sched: unknown value '%s' (lane | sorted | queued | warp)", value);
+    h->inited = false;
+  } else if (k == "policy") {
+    h->policy = atoi(value);
+  } else if (k == "refill") {
+    h->refill = atoi(value);
+    if (h->refill < 0) return fail(h, "refill must be >= 0");
+  } else if (k == "warp_slots") {
+    if (v == "auto")
+      h->warp_slots = 0;
+    else if (v == "64" || v == "96")
+      h->warp_slots = atoi(value);
+    else
+      return fail(h, "warp_slots: unknown value '%s' (auto | 64 | 96)", value);
     h->inited = false;
   } else if (k == "track_steps") {
     int t = atoi(value);
@@ -478,7 +542,7 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "tracking")
     v = h->tracking ? "local" : "global";
   else if (k == "exact")
-    v = std::to_string(h->sched == 2 ? h->exact : 1);
+    v = std::to_string(h->sched >= 2 ? h->exact : 1);
   else if (k == "russian_roulette")
     v = std::to_string(h->rr);
   else if (k == "max_bounces")
@@ -492,7 +556,13 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "counters")
     v = std::to_string(h->counters);
   else if (k == "sched")
-    v = h->sched == 2 ? "queued" : h->sched ? "sorted" : "lane";
+    v = h->sched == 3 ? "warp" : h->sched == 2 ? "queued" : h->sched ? "sorted" : "lane";
+  else if (k == "policy")
+    v = std::to_string(h->policy);
+  else if (k == "refill")
+    v = std::to_string(h->refill);
+  else if (k == "warp_slots")
+    v = std::to_string(effective_wslots(h));
   else if (k == "track_steps")
     v = std::to_string(h->track_steps);
   else if (k == "track_min_lanes")
@@ -586,6 +656,11 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   m.dcells = h->d_dcells;
   m.albedo = h->d_albedo;
   m.acells = h->d_acells;
+  {  // device footprint of the density lookups (selects the warp scheduler's slot count)
+    const int before = effective_wslots(h);
+    h->volume_bytes = h->layout == LAYOUT_CELL8 ? (size_t)(m.dnx + 1) * (m.dny + 1) * (m.dnz + 1) * 32 : nd * sizeof(float);
+    if (effective_wslots(h) != before) h->inited = false;  // another kernel instantiation
+  }
   h->scene_set = true;
   return 0;
 }

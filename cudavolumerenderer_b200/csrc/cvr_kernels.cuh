@@ -78,6 +78,8 @@ struct KernelParams {
   int track_steps;      // sorted scheduler: Woodcock steps per round
   int track_min_lanes;  // sorted scheduler: leave the step loop when fewer lanes are still tracking
   int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
+  int refill;           // warp scheduler: refill finished tracking lanes in place every n steps (0 = off)
+  int policy;           // warp scheduler: 0 = fullest state wins, 1 = events first unless a full tracking batch waits
 };
 
 // S_BOUNDARY_P = boundary event whose FIRST uniform is already drawn and parked in
@@ -1136,6 +1138,243 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     // ---------------------------------------------------------------- write back + push
     if (have) slot_store_dynamic(s_slot[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
     q_retire<N>(s_q, s_ctl, have, slot, R.state, lane);
+  }
+  flush_counters<COUNT>(P, C, lane);
+}
+
+// =============================================================================
+// Scheduler 4: warp-private wavefront ("warp").  ncu on the queued kernel (hetvol,
+// profiles/r1_scheduler_evolution.md) shows 39 % of all issued instructions in queue
+// management: four shared ring buffers per CTA with reserve / write / fence / ordered-CAS
+// commit / CAS pop.  Nothing of that is needed if a warp never shares paths: here every
+// warp owns CVR_WSLOTS path slots in shared memory and keeps the sort key of slot
+// (lane + 32 j) in register st[j].  One round =
+//   * ONE warp reduction (REDUX) of a packed byte-counter word gives the number of paths
+//     per state; the fullest state wins;
+//   * ballots + prefix popcounts rank the slots of that state; the first 32 write their id
+//     to a 32-byte list (same warp reads it back after a __syncwarp) -> lane i runs slot
+//     list[i], all lanes in the SAME state;
+//   * event (+ intersect) + Woodcock steps exactly as in the queued kernel;
+//   * the new key goes to a byte array the owner lanes read back.
+// No atomics (except the global path counter at regeneration), no fences, no CAS, no
+// block barriers; ~60 instructions of scheduling per batch instead of ~370.
+// Each path's own operation and RNG order is unchanged, so results are identical to the
+// other schedulers (event counters bit-identical, images up to fp32 atomic order).
+// =============================================================================
+#ifndef CVR_WMIN_BLOCKS
+#define CVR_WMIN_BLOCKS 3
+#endif
+enum : uint32_t { K_TRACK = 0, K_SCATTER = 1, K_BOUNDARY = 2, K_IDLE = 3, K_DONE = 4, K_BUSY = 5 };
+
+// dynamic shared memory of k_volpt_warp for a CTA of `block` threads with W slots per warp
+inline size_t warp_sched_smem_bytes(int block, int W) {
+  return (size_t)(block / 32) * (W * (sizeof(PathSlot) + 1) + 32);
+}
+
+// In-place refill of the tracking loop ("refill=n": every n Woodcock steps).  Lanes leave
+// the loop at ~13 % per step (collision or exit), so a batch that starts full is half empty
+// after five steps.  Instead of carrying the empty lanes, the finished lanes RETIRE their
+// path (dynamic part + new key) and take over a tracking-ready path of the same warp that
+// is waiting in a slot; lanes still tracking keep their registers.  Costs ~70 instructions
+// per refill against ~200 for ending the batch and forming a new one.
+// Returns the number of tracking-ready paths still waiting in slots.
+template <int K>
+CVR_DEV unsigned warp_refill(PathSlot* slots, uint8_t* keys, uint8_t* list, uint32_t (&st)[K], unsigned lane,
+                             unsigned lane_lt, bool& have, unsigned& slot, PathRegs<Xorwow>& R, uint32_t& meta_hi,
+                             const TrackInv& I, GridRay& G) {
+  const unsigned FULL = 0xffffffffu;
+  // 1. lanes whose path left the tracking state hand it back
+  if (have && R.state != S_TRACK) {
+    slot_store_dynamic(slots[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
+    keys[slot] = (uint8_t)sort_key(R.state);
+    have = false;
+    R.state = S_DONE;
+  }
+  __syncwarp();
+  // 2. owners pick up the new keys (slots that are still in a lane read back K_BUSY)
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (st[j] == K_BUSY) st[j] = keys[lane + 32 * j];
+  // 3. the i-th free lane takes the i-th tracking-ready slot
+  const unsigned free_m = __ballot_sync(FULL, !have);
+  const unsigned nfree = __popc(free_m);
+  unsigned base = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const bool mine = st[j] == K_TRACK;
+    const unsigned m = __ballot_sync(FULL, mine);
+    const unsigned r = base + __popc(m & lane_lt);
+    if (mine && r < nfree) {
+      list[r] = (uint8_t)(lane + 32 * j);
+      keys[lane + 32 * j] = (uint8_t)K_BUSY;
+      st[j] = K_BUSY;
+    }
+    base += __popc(m);
+  }
+  __syncwarp();
+  const unsigned ntake = min(base, nfree);
+  if (!have && (unsigned)__popc(free_m & lane_lt) < ntake) {
+    slot = list[__popc(free_m & lane_lt)];
+    slot_load_track(slots[slot], R);
+    have = true;
+    meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
+    G = grid_ray(I, R.o, R.d);
+  }
+  return base - ntake;
+}
+
+// W = path slots per warp: more slots -> fuller batches but less L1 next to the slots
+// (64: 125 KB of slots per SM at 3 CTAs, 96: 187 KB).  Measured on B200 (1024^2 x 16 spp,
+// Msamples/s, W = 64 / 96): hetvol 889 / 961, bucky 5031 / 5276 (volumes resident in L2:
+// fill wins), manix 2355 / 2102, fbm 512^3 1059 / 1031 (volumes beyond L2: L1 wins).
+template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64>
+__global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
+    k_volpt_warp(const __grid_constant__ KernelParams P) {
+  typedef Xorwow Rng;
+  constexpr int K = W / 32;
+  static_assert(W % 32 == 0 && K >= 1 && K <= 7, "slots per warp must be 32..224 in steps of 32");
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned lane_lt = (1u << lane) - 1u;
+
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  PathSlot* const slots = reinterpret_cast<PathSlot*>(s_raw) + warp * W;
+  uint8_t* const keys = s_raw + (size_t)nw * W * sizeof(PathSlot) + warp * W;
+  uint8_t* const list = s_raw + (size_t)nw * W * (sizeof(PathSlot) + 1) + warp * 32;
+
+  LaneCounters C;
+  const unsigned long long per_tile = P.path_end - P.path_begin;
+  const unsigned long long total = per_tile * P.n_launch_tiles;
+  const TrackInv& I = P.inv;
+
+  uint32_t st[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {  // all slots start idle
+    PathRegs<Rng> R;
+    R.o = v3(0, 0, 0), R.d = v3(0, 0, 1);
+    R.thr_x = R.thr_y = R.thr_z = 1.f;
+    R.t = R.dist = 0.f;
+    R.out_idx = R.path_lo = R.bounces = 0;
+    R.ncode = 0;
+    R.state = S_IDLE;
+    // per-slot stream (thread-rng mode)
+    R.rng.init((int32_t)(P.seed + (blockIdx.x * nw + warp) * W + lane + 32 * j));
+    slot_store(slots[lane + 32 * j], R);
+    st[j] = K_IDLE;
+  }
+  __syncwarp();
+  bool exhausted = false;
+
+  for (;;) {
+    // ---------------------------------------------------------------- census + choice
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) packed += st[j] < 4u ? (1u << (8u * st[j])) : 0u;
+    const uint32_t tot = __reduce_add_sync(FULL, packed);  // 4 byte counters, each <= 32 K
+    if (tot == 0u) break;                                  // every slot is DONE
+    const uint32_t c0 = tot & 255u, c1 = (tot >> 8) & 255u, c2 = (tot >> 16) & 255u, c3 = tot >> 24;
+    uint32_t key = 0, best = c0;
+    if (P.policy == 1 && c0 < 32u) best = 0;  // not a full tracking batch: run events first
+    if (c1 > best) best = c1, key = 1;
+    if (c2 > best) best = c2, key = 2;
+    if (c3 > best) best = c3, key = 3;
+
+    // ---------------------------------------------------------------- pick <= 32 slots of that state
+    unsigned base = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const bool mine = st[j] == key;
+      const unsigned m = __ballot_sync(FULL, mine);
+      const unsigned r = base + __popc(m & lane_lt);
+      if (mine && r < 32u) {
+        list[r] = (uint8_t)(lane + 32 * j);
+        keys[lane + 32 * j] = (uint8_t)K_BUSY;
+        st[j] = K_BUSY;
+      }
+      base += __popc(m);
+    }
+    __syncwarp();
+    const unsigned n = min(base, 32u);
+    bool have = lane < n;
+    unsigned slot = 0;
+    PathRegs<Rng> R;
+    R.state = S_DONE, R.ncode = 0, R.bounces = 0;
+    if (have) {
+      slot = list[lane];
+      if (key == 0)
+        slot_load_track(slots[slot], R);
+      else
+        slot_load(slots[slot], R);
+    }
+
+    // ---------------------------------------------------------------- event of this batch
+    if (key == 3) {
+      unsigned idle = __ballot_sync(FULL, have && R.state == S_IDLE);
+      if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
+    } else if (key == 1) {
+      if (have) do_scatter<LAYOUT, COUNT, FAST>(P, R, C);
+    } else if (key == 2) {
+      if (have) do_boundary<FAST>(P, R);
+    }
+    if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
+    // everything the tracking loop does not touch goes back to the slot now
+    if (key != 0 && have) slot_store_static(slots[slot], R);
+    uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
+
+    // ---------------------------------------------------------------- Woodcock steps
+    // tracking paths of this warp that are NOT in this batch: worth leaving the loop early
+    // for (they merge with the stragglers into a fuller batch)
+    bool others_track = (key == 0 ? c0 - n : c0) != 0u;
+    if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
+      GridRay G = grid_ray(I, R.o, R.d);
+#if CVR_PAIR
+      if (P.refill > 0 && others_track)  // top up the lanes this batch left empty
+        others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
+      for (int it = 0, since = 0; it < P.track_steps; it += 2, since += 2) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
+        if (P.refill > 0 && others_track && trk != FULL && (since >= P.refill || trk == 0)) {
+          others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
+          since = 0;
+          trk = __ballot_sync(FULL, R.state == S_TRACK);
+        }
+        if (trk == 0) break;
+        // few lanes left: without refill, stop if they can merge with waiting paths; with
+        // refill, stop once nothing is left to refill from (the events are waiting)
+        if (it > 0 && __popc(trk) < P.track_min_lanes && (others_track == (P.refill == 0))) break;
+        if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
+      }
+#else
+      for (int it = 0; it < P.track_steps; ++it) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+        if (trk == 0) break;
+        if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
+        if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
+      }
+#endif
+    } else {
+      float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
+      for (int it = 0; it < P.track_steps; ++it) {
+        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+        if (trk == 0) break;
+        if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
+        if (R.state == S_TRACK) {
+          if (LOCAL)
+            do_track_step_local<COUNT>(P, I, R, C, texit, mu);
+          else
+            do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- write back + new keys
+    if (have) {
+      slot_store_dynamic(slots[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
+      keys[slot] = (uint8_t)sort_key(R.state);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (st[j] == K_BUSY) st[j] = keys[lane + 32 * j];
   }
   flush_counters<COUNT>(P, C, lane);
 }

@@ -45,6 +45,15 @@ class Counters(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class VdbGridInfo(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 64), ("type", C.c_char * 64), ("channels", C.c_int32), ("compression", C.c_uint32),
+        ("file_version", C.c_uint32), ("bbox_min", C.c_int32 * 3), ("bbox_max", C.c_int32 * 3), ("dim", C.c_int32 * 3),
+        ("background", C.c_float * 3), ("active_voxels", C.c_uint64), ("leaf_count", C.c_uint64),
+        ("active_tiles", C.c_uint64),
+    ]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [
         ("res_x", C.c_uint32), ("res_y", C.c_uint32),
@@ -98,6 +107,15 @@ SYMBOLS = [
     ("cvr_debug_lookup", C.c_int, [H, f32p, C.c_int, f32p, f32p]),
     ("cvr_gather_roofline", C.c_int, [H, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("cvr_synth_volume", C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, f32p, f32p, f32p]),
+    ("cvr_vdb_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("cvr_vdb_close", C.c_int, [C.c_void_p]),
+    ("cvr_vdb_last_error", C.c_char_p, []),
+    ("cvr_vdb_grid_count", C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    ("cvr_vdb_grid_info", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    ("cvr_vdb_grid_meta", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("cvr_vdb_densify", C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, f32p, f32p, C.c_uint64]),
+    ("cvr_vdb_leaves", C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_uint64), f32p]),
 ]
 
 _lib = None

@@ -50,6 +50,7 @@ struct cvr_renderer {
   int counters = 1;
   int sched = 3;  // 0 = lane-persistent, 1 = block-sorted wavefront, 2 = queued wavefront, 3 = warp-private wavefront
   int policy = 0; // warp scheduler batch choice (KernelParams::policy)
+  int pair = -1;  // speculative second Woodcock step: -1 = auto (on while the density layout fits the L2), 0, 1
   int refill = 0; // warp scheduler: in-place refill period of the tracking loop in steps (0 = off)
   size_t smem_bytes = 0;  // dynamic shared memory of the selected kernel
   int warp_slots = 0;     // warp scheduler: path slots per warp (64 | 96), 0 = auto
@@ -230,6 +231,13 @@ int effective_wslots(cvr_handle h) {
   return (h->volume_bytes && h->volume_bytes <= (size_t)h->l2_bytes) ? 96 : 64;
 }
 
+// The speculative second step doubles the loads in flight per lane (latency) at the price of
+// ~14 % extra lookups (bandwidth): on while the density layout is L2-resident, off beyond.
+int effective_pair(cvr_handle h) {
+  if (h->pair >= 0) return h->pair;
+  return (h->volume_bytes && h->volume_bytes <= (size_t)h->l2_bytes) ? 1 : 0;
+}
+
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
   kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
@@ -319,6 +327,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.fix_nan = h->fix_nan;
   P.policy = h->policy;
   P.refill = h->refill;
+  P.pair = effective_pair(h);
   P.rr = h->rr;
   P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
@@ -503,6 +512,8 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     h->inited = false;
   } else if (k == "policy") {
     h->policy = atoi(value);
+  } else if (k == "pair") {
+    h->pair = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
   } else if (k == "refill") {
     h->refill = atoi(value);
     if (h->refill < 0) return fail(h, "refill must be >= 0");
@@ -561,6 +572,8 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(h->policy);
   else if (k == "refill")
     v = std::to_string(h->refill);
+  else if (k == "pair")
+    v = std::to_string(effective_pair(h));
   else if (k == "warp_slots")
     v = std::to_string(effective_wslots(h));
   else if (k == "track_steps")

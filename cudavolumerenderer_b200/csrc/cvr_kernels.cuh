@@ -78,6 +78,7 @@ struct KernelParams {
   int track_steps;      // sorted scheduler: Woodcock steps per round
   int track_min_lanes;  // sorted scheduler: leave the step loop when fewer lanes are still tracking
   int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
+  int pair;             // fast tracking loop: two Woodcock steps per iteration, the second speculative
   int refill;           // warp scheduler: refill finished tracking lanes in place every n steps (0 = off)
   int policy;           // warp scheduler: 0 = fullest state wins, 1 = events first unless a full tracking batch waits
 };
@@ -904,12 +905,6 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 #ifndef CVR_QSLOTS
 #define CVR_QSLOTS 512
 #endif
-#ifndef CVR_PAIR
-#define CVR_PAIR 1  // fast tracking loop: two Woodcock steps per iteration, second one speculative
-#endif
-#ifndef CVR_VOTE_EVERY
-#define CVR_VOTE_EVERY 1  // Woodcock steps between two warp votes of the fast tracking loop
-#endif
 
 struct QueueCtl {
   unsigned int head[4];  // pop cursor
@@ -1089,8 +1084,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     // ---------------------------------------------------------------- Woodcock steps
     if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
       const GridRay G = grid_ray(I, R.o, R.d);
-#if CVR_PAIR
-      for (int it = 0; it < P.track_steps; it += 2) {
+      for (int it = 0; it < P.track_steps; it += P.pair ? 2 : 1) {
         unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
         if (trk == 0) break;
         if (it > 0 && __popc(trk) < P.track_min_lanes) {
@@ -1098,22 +1092,13 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
           if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
           if (__shfl_sync(FULL, waiting, 0) != 0u) break;
         }
-        if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
-      }
-#else
-      for (int it = 0; it < P.track_steps; it += CVR_VOTE_EVERY) {
-        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
-        if (trk == 0) break;
-        if (it > 0 && __popc(trk) < P.track_min_lanes) {
-          unsigned waiting = 0;
-          if (lane == 0) waiting = ld_volatile_u32(&s_ctl.tail[0]) - ld_volatile_u32(&s_ctl.head[0]);
-          if (__shfl_sync(FULL, waiting, 0) != 0u) break;
+        if (R.state == S_TRACK) {
+          if (P.pair)
+            track_pair_fast<COUNT>(P, I, G, R, C);
+          else
+            track_step_fast<COUNT>(P, I, G, R, C);
         }
-#pragma unroll
-        for (int s = 0; s < CVR_VOTE_EVERY; ++s)
-          if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
       }
-#endif
     } else {
       float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
       for (int it = 0; it < P.track_steps; ++it) {
@@ -1327,30 +1312,30 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
     bool others_track = (key == 0 ? c0 - n : c0) != 0u;
     if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
       GridRay G = grid_ray(I, R.o, R.d);
-#if CVR_PAIR
-      if (P.refill > 0 && others_track)  // top up the lanes this batch left empty
-        others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
-      for (int it = 0, since = 0; it < P.track_steps; it += 2, since += 2) {
-        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
-        if (P.refill > 0 && others_track && trk != FULL && (since >= P.refill || trk == 0)) {
+      if (P.pair) {
+        if (P.refill > 0 && others_track)  // top up the lanes this batch left empty
           others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
-          since = 0;
-          trk = __ballot_sync(FULL, R.state == S_TRACK);
+        for (int it = 0, since = 0; it < P.track_steps; it += 2, since += 2) {
+          unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
+          if (P.refill > 0 && others_track && trk != FULL && (since >= P.refill || trk == 0)) {
+            others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
+            since = 0;
+            trk = __ballot_sync(FULL, R.state == S_TRACK);
+          }
+          if (trk == 0) break;
+          // few lanes left: without refill, stop if they can merge with waiting paths; with
+          // refill, stop once nothing is left to refill from (the events are waiting)
+          if (it > 0 && __popc(trk) < P.track_min_lanes && (others_track == (P.refill == 0))) break;
+          if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
         }
-        if (trk == 0) break;
-        // few lanes left: without refill, stop if they can merge with waiting paths; with
-        // refill, stop once nothing is left to refill from (the events are waiting)
-        if (it > 0 && __popc(trk) < P.track_min_lanes && (others_track == (P.refill == 0))) break;
-        if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
+      } else {
+        for (int it = 0; it < P.track_steps; ++it) {
+          unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+          if (trk == 0) break;
+          if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
+          if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
+        }
       }
-#else
-      for (int it = 0; it < P.track_steps; ++it) {
-        unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
-        if (trk == 0) break;
-        if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
-        if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
-      }
-#endif
     } else {
       float texit = -1.0f, mu = 0.0f;  // local-majorant brick of this lane (recomputed on entry)
       for (int it = 0; it < P.track_steps; ++it) {

@@ -39,6 +39,24 @@ def fbm(n: int = 256, seed: int = 0, albedo: float = 0.99) -> Scene:
                  albedo_const=(albedo,) * 3, name=f"fbm{n}")
 
 
+def from_vdb(path: str) -> Scene:
+    """VDBSceneBuilder (VDBSceneBuilder.h:40-80): density FloatGrid + albedo Vec3SGrid densified
+    over the density grid's active bounding box, max_density = max voxel, the file's world
+    box read and ignored (box fixed to +-0.5, Q4), scale 100, default camera (fov 0.7)."""
+    from .vdb import VdbFile
+
+    with VdbFile(path) as f:
+        den = f.densify("density", inactive=(0.0, 0.0, 0.0))
+        alb_grid = f.grid("albedo")  # raises "VDB file does not contain an albedo grid"
+        if alb_grid["dim"] != f.grid("density")["dim"]:
+            # the reference indexes the albedo array with the ALBEDO box but sizes the volume with
+            # the DENSITY resolution (VDBSceneBuilder.h:47-67): only defined when they agree
+            raise abi.CvrError("density and albedo grids have different active bounding boxes")
+        alb = f.densify("albedo", out_channels=4, inactive=(0.0, 0.0, 0.0))
+    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=float(den.max()), fov_x=0.7,
+                 name=path.rsplit("/", 1)[-1])
+
+
 SCENES = {"bucky": bucky, "hetvol": hetvol, "manix": manix, "fbm": fbm}
 
 

@@ -23,7 +23,9 @@ using namespace cvr;
 
 namespace {
 
-enum Variant { VAR_NAIVE = 0, VAR_REGEN = 1, VAR_STREAM = 2 };
+// VAR_STREAM_MK = streamingMK: Rng(c_seed + path_id) per path (StreamingVolPTmk_kernel.cuh:55),
+// pull-back at scatter (:194), seed += n_paths per reset (RenderKernelLauncher.cu:480-481)
+enum Variant { VAR_NAIVE = 0, VAR_REGEN = 1, VAR_STREAM = 2, VAR_STREAM_MK = 3 };
 
 thread_local std::string g_create_error;
 
@@ -329,7 +331,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.refill = h->refill;
   P.pair = effective_pair(h);
   P.rr = h->rr;
-  P.pullback = (h->variant == VAR_NAIVE || h->variant == VAR_STREAM) ? 1 : 0;
+  P.pullback = (h->variant != VAR_REGEN) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
   kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
@@ -377,9 +379,17 @@ int cvr_create(const char* kernel_name, int device, cvr_handle* out) {
     variant = VAR_REGEN;
   else if (k == "streamingSK")
     variant = VAR_STREAM;
+  else if (k == "sortingSK")  // same estimator, streams and seed rule as streamingSK (SortingVolPTsk_kernel.cuh:227-230,
+    variant = VAR_STREAM;     // :314; RenderKernelLauncher.cu:664-665); its Morton ordering is scheduling, which is ours
+  else if (k == "streamingMK")
+    variant = VAR_STREAM_MK;
+  else if (k == "naiveMK")
+    return fail(nullptr,
+                "cvr_create: kernel 'naiveMK' is not offered: its per-bounce reseeding and first-hit handling "
+                "(NaiveVolPTmk_kernel.cuh:32-75,90) make it a different estimator variant; use naiveSK");
   else
     return fail(nullptr,
-                "cvr_create: unknown kernel '%s' (naiveSK | regenerationSK | streamingSK)",
+                "cvr_create: unknown kernel '%s' (naiveSK | regenerationSK | streamingSK | streamingMK | sortingSK)",
                 kernel_name);
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -778,7 +788,7 @@ int cvr_reset(cvr_handle h) {
   CVR_CUDA(h, cudaStreamSynchronize(h->stream));
   // RenderKernelLauncher.cu:353-361 (regeneration: seed_ += n_paths_), :567-575 (streaming: seed_++)
   uint32_t n_paths = (uint32_t)(h->P.cam.res_x * h->P.cam.res_y) * h->iterations;
-  if (h->variant == VAR_REGEN) h->seed += n_paths;
+  if (h->variant == VAR_REGEN || h->variant == VAR_STREAM_MK) h->seed += n_paths;
   if (h->variant == VAR_STREAM) h->seed += 1;
   return 0;
 }
@@ -912,7 +922,7 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
   const uint32_t n_paths_tile = (uint32_t)tile_px * r->iterations;  // uint, RenderKernelLauncher.cu:125
   // stream base of global tile k = seed0 + k * step, i.e. what reset() accumulates on one GPU
   const uint32_t seed0 = h->variant == VAR_NAIVE ? 0u : h->seed;
-  const uint32_t seed_step = h->variant == VAR_REGEN ? n_paths_tile : h->variant == VAR_STREAM ? 1u : 0u;
+  const uint32_t seed_step = (h->variant == VAR_REGEN || h->variant == VAR_STREAM_MK) ? n_paths_tile : h->variant == VAR_STREAM ? 1u : 0u;
   unsigned long long pb, pe;
   path_range(h, pb, pe);
   const float scale = (float)r->iterations;  // UtilityFunctors::Scale(current_iteration_)

@@ -151,7 +151,9 @@ inline std::unique_ptr<AbstractProgressiveRenderer> createRenderer(const std::st
   if (kernel == "naiveSK") return std::make_unique<CudaVolPath<NaiveVolPTsk>>(scene, tiling, iterations, device);
   if (kernel == "regenerationSK") return std::make_unique<CudaVolPath<RegenerationVolPTsk>>(scene, tiling, iterations, device);
   if (kernel == "streamingSK") return std::make_unique<CudaVolPath<StreamingVolPTsk>>(scene, tiling, iterations, device);
-  throw std::runtime_error("kernel '" + kernel + "' is not available in this build (naiveSK | regenerationSK | streamingSK)");
+  if (kernel == "streamingMK") return std::make_unique<CudaVolPath<StreamingVolPTmk>>(scene, tiling, iterations, device);
+  if (kernel == "sortingSK") return std::make_unique<CudaVolPath<SortingVolPTsk>>(scene, tiling, iterations, device);
+  throw std::runtime_error("kernel '" + kernel + "' is not available in this build (naiveSK | regenerationSK | streamingSK | streamingMK | sortingSK)");
 }
 
 }  // namespace cvrhost

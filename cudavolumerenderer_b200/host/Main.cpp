@@ -44,7 +44,7 @@ void usage() {
                "  --interactive arg (=1)        run the interactive view (not available in this build)\n"
                "  --trials arg (=1)             number of times to run the algorithm\n"
                "  -a [ --algorithm ] arg (=cudaVolPath)\n"
-               "  -k [ --kernel ] arg (=regenerationSK)   naiveSK | regenerationSK | streamingSK\n"
+               "  -k [ --kernel ] arg (=regenerationSK)   naiveSK | regenerationSK | streamingSK | streamingMK | sortingSK\n"
                "  --number-of-tiles arg (=1 1)\n"
                "  --use-unified-memory arg (=0)\n"
                "  --device arg (=0)             CUDA device\n"

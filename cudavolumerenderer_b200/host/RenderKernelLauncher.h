@@ -76,5 +76,11 @@ struct RegenerationVolPTsk : VolPTKernelLauncher {
 struct StreamingVolPTsk : VolPTKernelLauncher {
   explicit StreamingVolPTsk(int device = 0) : VolPTKernelLauncher("streamingSK", device) {}
 };
+struct StreamingVolPTmk : VolPTKernelLauncher {  // RenderKernelLauncher.h:115-137
+  explicit StreamingVolPTmk(int device = 0) : VolPTKernelLauncher("streamingMK", device) {}
+};
+struct SortingVolPTsk : VolPTKernelLauncher {  // RenderKernelLauncher.h:153-170
+  explicit SortingVolPTsk(int device = 0) : VolPTKernelLauncher("sortingSK", device) {}
+};
 
 }  // namespace cvrhost

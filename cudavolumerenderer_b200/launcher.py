@@ -264,7 +264,22 @@ class StreamingVolPTsk(VolPTKernelLauncher):
     KERNEL = "streamingSK"
 
 
-KERNELS = {"naiveSK": NaiveVolPTsk, "regenerationSK": RegenerationVolPTsk, "streamingSK": StreamingVolPTsk}
+class StreamingVolPTmk(VolPTKernelLauncher):
+    """-k streamingMK (RenderKernelLauncher.h:115-137; StreamingVolPTmk_kernel.cuh): per-path streams
+    Rng(c_seed + path_id) (:55), pull-back at scatter (:194), seed += n_paths per reset
+    (RenderKernelLauncher.cu:480-481).  One persistent kernel here, not one launch per bounce."""
+    KERNEL = "streamingMK"
+
+
+class SortingVolPTsk(VolPTKernelLauncher):
+    """-k sortingSK (RenderKernelLauncher.h:153-170; SortingVolPTsk_kernel.cuh): the streamingSK
+    estimator, streams and seed rule (:227-230, :314; RenderKernelLauncher.cu:664-665); its Morton
+    ordering of rays is a scheduling choice, which belongs to this library."""
+    KERNEL = "sortingSK"
+
+
+KERNELS = {"naiveSK": NaiveVolPTsk, "regenerationSK": RegenerationVolPTsk, "streamingSK": StreamingVolPTsk,
+           "streamingMK": StreamingVolPTmk, "sortingSK": SortingVolPTsk}
 
 
 def createLauncher(kernel: str, device: int = 0, **options) -> VolPTKernelLauncher:

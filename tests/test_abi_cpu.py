@@ -100,6 +100,7 @@ def test_gpu_entry_points_fail_loudly_without_a_device(lib):
 def test_kernel_names_follow_reference_config(lib):
     from cudavolumerenderer_b200 import KERNELS, createLauncher
 
-    assert set(KERNELS) == {"naiveSK", "regenerationSK", "streamingSK"}
+    # Config::getKernelNamesOrderedVector (Config.h:210-213) minus naiveMK (a different estimator variant)
+    assert set(KERNELS) == {"naiveSK", "regenerationSK", "streamingSK", "streamingMK", "sortingSK"}
     with pytest.raises(ValueError):
         createLauncher("cpuSK")

@@ -45,6 +45,16 @@ class Counters(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class SparseDesc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32 * 3), ("bbox_min", C.c_int32 * 3), ("n_leaves", C.c_uint64),
+        ("leaf_origins", C.c_void_p), ("leaf_values", C.c_void_p),
+        ("albedo_const", C.c_float * 3), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3),
+        ("scale", C.c_float), ("max_density", C.c_float), ("hg_g", C.c_float),
+        ("ggx_alpha", C.c_float * 2), ("ggx_eta", C.c_float),
+    ]
+
+
 class VdbGridInfo(C.Structure):
     _fields_ = [
         ("name", C.c_char * 64), ("type", C.c_char * 64), ("channels", C.c_int32), ("compression", C.c_uint32),
@@ -107,6 +117,9 @@ SYMBOLS = [
     ("cvr_debug_lookup", C.c_int, [H, f32p, C.c_int, f32p, f32p]),
     ("cvr_gather_roofline", C.c_int, [H, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("cvr_synth_volume", C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, f32p, f32p, f32p]),
+    ("cvr_set_scene_sparse", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("cvr_set_scene_procedural", C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_uint32, C.c_void_p, f32p]),
+    ("cvr_get_volume_info", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     ("cvr_vdb_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     ("cvr_vdb_close", C.c_int, [C.c_void_p]),
     ("cvr_vdb_last_error", C.c_char_p, []),

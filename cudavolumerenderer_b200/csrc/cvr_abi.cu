@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "cvr_kernels.cuh"
+#include "cvr_volume.cuh"
 
 using namespace cvr;
 
@@ -42,7 +43,8 @@ struct cvr_renderer {
 
   // options
   int rng_mode = RNG_XORWOW_PATH;
-  int layout = LAYOUT_CELL8;
+  int layout = LAYOUT_CELL8;        // option "layout": how cvr_set_scene lays a DENSE volume out
+  int scene_layout = LAYOUT_CELL8;  // layout of the scene in place (LAYOUT_BRICK after a sparse / procedural-sparse scene)
   int exact = 0;  // 0 = fused arithmetic (queued scheduler only), 1 = the reference's operation order
   int rr = 1;
   uint32_t max_bounces = 1u << 20;
@@ -79,6 +81,8 @@ struct cvr_renderer {
   float4* d_acells = nullptr;
   float* d_majorant = nullptr;
   uint32_t maj_dim[3] = {0, 0, 0};
+  uint32_t* d_btable = nullptr;  // brick layout: slot table over the brick grid
+  uint64_t n_bricks = 0;         // brick layout: stored bricks (without the zero brick)
   unsigned long long* d_head = nullptr;
   DeviceCounters* d_ctr = nullptr;
   bool allocated = false;
@@ -130,6 +134,18 @@ typedef void (*kernel_fn)(const KernelParams);
 
 template <int W>
 kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int tracking) {
+  if (layout == LAYOUT_BRICK) {  // sparse bricks: fused arithmetic only, global or local majorant
+#define CVR_KB(R, LOCAL)                                                                              \
+  if (rng_mode == R && tracking == LOCAL)                                                             \
+    return count ? (kernel_fn)k_volpt_warp<R, LAYOUT_BRICK, true, true, LOCAL != 0, W>                  \
+                 : (kernel_fn)k_volpt_warp<R, LAYOUT_BRICK, false, true, LOCAL != 0, W>;
+    CVR_KB(RNG_XORWOW_PATH, 0)
+    CVR_KB(RNG_XORWOW_PATH, 1)
+    CVR_KB(RNG_XORWOW_THREAD, 0)
+    CVR_KB(RNG_XORWOW_THREAD, 1)
+#undef CVR_KB
+    return nullptr;
+  }
   if (tracking == 1) {
     if (layout != LAYOUT_CELL8) return nullptr;
     if (rng_mode == RNG_XORWOW_PATH)
@@ -203,13 +219,24 @@ int set_device(cvr_handle h) {
   return 0;
 }
 
+// Volume memory comes from the device's stream-ordered pool with an unlimited release
+// threshold: cudaMalloc / cudaFree of 10^8-byte blocks cost anything between 5 and 250 ms per
+// cvr_set_scene on this driver (measured), the pool hands the same blocks back in microseconds.
+cudaError_t vol_alloc(cvr_handle h, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, h->stream); }
+void vol_free(cvr_handle h, void* p) {
+  if (p) cudaFreeAsync(p, h->stream);
+}
+
 void free_volume(cvr_handle h) {
-  cudaFree(h->d_density);
-  cudaFree(h->d_dcells);
-  cudaFree(h->d_albedo);
-  cudaFree(h->d_acells);
-  cudaFree(h->d_majorant);
+  vol_free(h, h->d_density);
+  vol_free(h, h->d_dcells);
+  vol_free(h, h->d_albedo);
+  vol_free(h, h->d_acells);
+  vol_free(h, h->d_majorant);
+  vol_free(h, h->d_btable);
   h->d_majorant = nullptr;
+  h->d_btable = nullptr;
+  h->n_bricks = 0;
   h->d_density = h->d_dcells = nullptr;
   h->d_albedo = h->d_acells = nullptr;
   h->scene_set = false;
@@ -242,8 +269,10 @@ int effective_pair(cvr_handle h) {
 
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
-  if (!k) return fail(h, "no kernel for sched=%d rng=%d layout=%d (philox needs sched=lane)", h->sched, h->rng_mode, h->layout);
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h));
+  if (!k)
+    return fail(h, "no kernel for sched=%d rng=%d layout=%d exact=%d (philox needs sched=lane; sparse scenes need sched=warp, exact=0)",
+                h->sched, h->rng_mode, h->scene_layout, h->exact);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
@@ -334,7 +363,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.pullback = (h->variant != VAR_REGEN) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->layout, h->counters, h->exact, h->tracking, effective_wslots(h));
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h));
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
@@ -413,6 +442,12 @@ int cvr_create(const char* kernel_name, int device, cvr_handle* out) {
   cudaGetDeviceProperties(&prop, device);
   h->sm_count = prop.multiProcessorCount;
   h->l2_bytes = prop.l2CacheSize;
+  {
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   if (prop.major < 10) {
     fail(nullptr, "cvr_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
          prop.major, prop.minor);
@@ -619,7 +654,9 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   if (set_device(h)) return 1;
   CVR_CUDA(h, cudaStreamSynchronize(h->stream));
   free_volume(h);
+  h->scene_layout = h->layout;
   MediumParams& m = h->P.med;
+  m.btable = nullptr, m.bmx = m.bmy = m.bmz = 0;
   m.box_min = V3{s->box_min[0], s->box_min[1], s->box_min[2]};
   m.box_max = V3{s->box_max[0], s->box_max[1], s->box_max[2]};
   m.scale = s->scale;
@@ -631,13 +668,13 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   m.dnx = s->density_dim[0], m.dny = s->density_dim[1], m.dnz = s->density_dim[2];
   const cudaMemcpyKind kind = s->density_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   size_t nd = (size_t)m.dnx * m.dny * m.dnz;
-  CVR_CUDA(h, cudaMalloc(&h->d_density, nd * sizeof(float)));
+  CVR_CUDA(h, vol_alloc(h, (void**)&h->d_density, nd * sizeof(float)));
   CVR_CUDA(h, cudaMemcpyAsync(h->d_density, s->density, nd * sizeof(float), kind, h->stream));
   const int bt = 256;
   if (h->layout == LAYOUT_CELL8) {
     size_t ncell = (size_t)(m.dnx + 1) * (m.dny + 1) * (m.dnz + 1);
     if (ncell >= (1ull << 32)) return fail(h, "cvr_set_scene: density grid too large for 32-bit cell indices");
-    CVR_CUDA(h, cudaMalloc(&h->d_dcells, ncell * 8 * sizeof(float)));
+    CVR_CUDA(h, vol_alloc(h, (void**)&h->d_dcells, ncell * 8 * sizeof(float)));
     int g = (int)std::min<size_t>((ncell + bt - 1) / bt, (size_t)h->sm_count * 32);
     k_build_density_cells<<<g, bt, 0, h->stream>>>(h->d_density, m.dnx, m.dny, m.dnz, (float4*)h->d_dcells);
     CVR_CUDA(h, cudaGetLastError());
@@ -646,7 +683,7 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     h->maj_dim[1] = (uint32_t)(m.dny + 1 + CVR_BRICK - 1) / CVR_BRICK;
     h->maj_dim[2] = (uint32_t)(m.dnz + 1 + CVR_BRICK - 1) / CVR_BRICK;
     size_t n_bricks = (size_t)h->maj_dim[0] * h->maj_dim[1] * h->maj_dim[2];
-    CVR_CUDA(h, cudaMalloc(&h->d_majorant, n_bricks * sizeof(float)));
+    CVR_CUDA(h, vol_alloc(h, (void**)&h->d_majorant, n_bricks * sizeof(float)));
     k_build_majorant<<<(unsigned)((n_bricks * 32 + bt - 1) / bt), bt, 0, h->stream>>>(
         (const float4*)h->d_dcells, m.dnx, m.dny, m.dnz, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2], h->d_majorant);
     CVR_CUDA(h, cudaGetLastError());
@@ -657,11 +694,11 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   if (s->albedo) {
     m.anx = s->albedo_dim[0], m.any = s->albedo_dim[1], m.anz = s->albedo_dim[2];
     size_t na = (size_t)m.anx * m.any * m.anz;
-    CVR_CUDA(h, cudaMalloc(&h->d_albedo, na * sizeof(float4)));
+    CVR_CUDA(h, vol_alloc(h, (void**)&h->d_albedo, na * sizeof(float4)));
     CVR_CUDA(h, cudaMemcpyAsync(h->d_albedo, s->albedo, na * sizeof(float4), kind, h->stream));
     if (h->layout == LAYOUT_CELL8) {
       size_t ncell = (size_t)(m.anx + 1) * (m.any + 1) * (m.anz + 1);
-      CVR_CUDA(h, cudaMalloc(&h->d_acells, ncell * 8 * sizeof(float4)));
+      CVR_CUDA(h, vol_alloc(h, (void**)&h->d_acells, ncell * 8 * sizeof(float4)));
       int g = (int)std::min<size_t>((ncell * 8 + bt - 1) / bt, (size_t)h->sm_count * 32);
       k_build_albedo_cells<<<g, bt, 0, h->stream>>>(h->d_albedo, m.anx, m.any, m.anz, h->d_acells);
       CVR_CUDA(h, cudaGetLastError());
@@ -670,8 +707,8 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   if (h->layout == LAYOUT_CELL8) {
     // the dense copies are only the source of the cell layouts
     CVR_CUDA(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_density);
-    cudaFree(h->d_albedo);
+    vol_free(h, h->d_density);
+    vol_free(h, h->d_albedo);
     h->d_density = nullptr;
     h->d_albedo = nullptr;
   }
@@ -685,6 +722,177 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     if (effective_wslots(h) != before) h->inited = false;  // another kernel instantiation
   }
   h->scene_set = true;
+  return 0;
+}
+
+extern "C++" {
+namespace {
+
+// medium scalars shared by the sparse / procedural scene setters
+void set_medium_scalars(cvr_handle h, const float box_min[3], const float box_max[3], float scale, float hg_g,
+                        const float ggx_alpha[2], float ggx_eta, const float albedo_const[3]) {
+  MediumParams& m = h->P.med;
+  m.box_min = V3{box_min[0], box_min[1], box_min[2]};
+  m.box_max = V3{box_max[0], box_max[1], box_max[2]};
+  m.scale = scale;
+  m.hg_g = hg_g;
+  m.alpha_x = ggx_alpha && ggx_alpha[0] > 0.f ? ggx_alpha[0] : 0.1f;
+  m.alpha_y = ggx_alpha && ggx_alpha[1] > 0.f ? ggx_alpha[1] : 0.1f;
+  m.eta = ggx_eta > 0.f ? ggx_eta : 1.05f / 1.01f;
+  m.albedo_const = 1;
+  m.albedo_r = albedo_const[0], m.albedo_g = albedo_const[1], m.albedo_b = albedo_const[2];
+  m.anx = m.any = m.anz = 2;
+  m.density = nullptr, m.albedo = nullptr, m.acells = nullptr;
+}
+
+// bricks + slot table + majorant grid from a voxel accessor; returns the maximum voxel value
+template <class Acc>
+int build_bricks(cvr_handle h, const Acc& acc, int nx, int ny, int nz, float* max_value) {
+  MediumParams& m = h->P.med;
+  m.dnx = nx, m.dny = ny, m.dnz = nz;
+  const uint32_t bmx = (uint32_t)(nx + 1 + 7) / 8, bmy = (uint32_t)(ny + 1 + 7) / 8, bmz = (uint32_t)(nz + 1 + 7) / 8;
+  const size_t nb = (size_t)bmx * bmy * bmz;
+  if (nb >= (1ull << 31)) return fail(h, "sparse scene: brick grid too large");
+  uint32_t* d_counter = nullptr;
+  CVR_CUDA(h, vol_alloc(h, (void**)&h->d_btable, nb * sizeof(uint32_t)));
+  CVR_CUDA(h, cudaMalloc(&d_counter, 2 * sizeof(uint32_t)));
+  CVR_CUDA(h, cudaMemsetAsync(d_counter, 0, 2 * sizeof(uint32_t), h->stream));
+  const int bt = 256;
+  const int g = (int)std::min<size_t>((nb + bt - 1) / bt, (size_t)h->sm_count * 32);
+  k_brick_slots_fn<<<g, bt, 0, h->stream>>>(acc, nx, ny, nz, bmx, bmy, bmz, h->d_btable, d_counter);
+  CVR_CUDA(h, cudaGetLastError());
+  uint32_t n_slots = 0;
+  CVR_CUDA(h, cudaMemcpyAsync(&n_slots, d_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_bricks = n_slots;
+  const size_t brick_floats = 512 * 8;
+  cudaError_t e = vol_alloc(h, (void**)&h->d_dcells, ((size_t)n_slots + 1) * brick_floats * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(d_counter);
+    return fail(h, "sparse scene: %u bricks (%.1f GB) do not fit: %s", n_slots,
+                ((double)n_slots + 1) * brick_floats * 4 / 1e9, cudaGetErrorString(e));
+  }
+  CVR_CUDA(h, cudaMemsetAsync(h->d_dcells, 0, brick_floats * sizeof(float), h->stream));  // slot 0 = the zero brick
+  // one CTA per brick-grid entry: grid.x = one z-slice of the brick grid, grid.y = slices
+  k_build_bricks_fn<<<dim3(bmx * bmy, bmz), 512, 0, h->stream>>>(acc, nx, ny, nz, bmx, bmy, h->d_btable,
+                                                                (float4*)h->d_dcells, n_slots);
+  CVR_CUDA(h, cudaGetLastError());
+  h->maj_dim[0] = bmx, h->maj_dim[1] = bmy, h->maj_dim[2] = bmz;
+  CVR_CUDA(h, vol_alloc(h, (void**)&h->d_majorant, nb * sizeof(float)));
+  k_brick_majorant<<<(unsigned)((nb * 32 + bt - 1) / bt), bt, 0, h->stream>>>(h->d_btable, (const float4*)h->d_dcells, nb,
+                                                                                h->d_majorant, d_counter + 1);
+  CVR_CUDA(h, cudaGetLastError());
+  uint32_t max_bits = 0;
+  CVR_CUDA(h, cudaMemcpyAsync(&max_bits, d_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_counter);
+  std::memcpy(max_value, &max_bits, 4);
+  m.dcells = h->d_dcells;
+  m.btable = h->d_btable;
+  m.bmx = bmx, m.bmy = bmy, m.bmz = bmz;
+  h->scene_layout = LAYOUT_BRICK;
+  h->volume_bytes = ((size_t)n_slots + 1) * brick_floats * sizeof(float) + nb * sizeof(uint32_t);
+  h->inited = false;
+  return 0;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int cvr_set_scene_sparse(cvr_handle h, const cvr_sparse_desc* s) {
+  CVR_CHECK_HANDLE(h);
+  if (!s || !s->leaf_origins || !s->leaf_values || s->n_leaves == 0) return fail(h, "cvr_set_scene_sparse: no leaves");
+  if (s->dim[0] < 2 || s->dim[1] < 2 || s->dim[2] < 2) return fail(h, "cvr_set_scene_sparse: grid dims must be >= 2");
+  if (!(s->scale > 0.f)) return fail(h, "cvr_set_scene_sparse: scale must be positive");
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_volume(h);
+  set_medium_scalars(h, s->box_min, s->box_max, s->scale, s->hg_g, s->ggx_alpha, s->ggx_eta, s->albedo_const);
+  // leaf grid: absolute index space from the multiple of 8 at or below bbox_min
+  int base[3], off[3], lb[3];
+  for (int a = 0; a < 3; ++a) {
+    base[a] = (int)std::floor(s->bbox_min[a] / 8.0) * 8;
+    off[a] = s->bbox_min[a] - base[a];
+    lb[a] = (off[a] + s->dim[a] + 7) / 8;
+  }
+  const size_t n_table = (size_t)lb[0] * lb[1] * lb[2];
+  int32_t* d_org = nullptr;
+  float* d_val = nullptr;
+  uint32_t* d_tab = nullptr;
+  CVR_CUDA(h, vol_alloc(h, (void**)&d_org, s->n_leaves * 3 * sizeof(int32_t)));
+  CVR_CUDA(h, vol_alloc(h, (void**)&d_val, s->n_leaves * 512 * sizeof(float)));
+  CVR_CUDA(h, vol_alloc(h, (void**)&d_tab, n_table * sizeof(uint32_t)));
+  CVR_CUDA(h, cudaMemcpyAsync(d_org, s->leaf_origins, s->n_leaves * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CVR_CUDA(h, cudaMemcpyAsync(d_val, s->leaf_values, s->n_leaves * 512 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CVR_CUDA(h, cudaMemsetAsync(d_tab, 0, n_table * sizeof(uint32_t), h->stream));
+  k_fill_leaf_table<<<(unsigned)((s->n_leaves + 255) / 256), 256, 0, h->stream>>>(d_org, s->n_leaves, base[0], base[1], base[2],
+                                                                                   lb[0], lb[1], lb[2], d_tab);
+  CVR_CUDA(h, cudaGetLastError());
+  LeafVolumeAccessor acc{LeafAccessor{d_tab, d_val, lb[0], lb[1], lb[2], off[0], off[1], off[2]}};
+  float mx = 0.f;
+  int rc = build_bricks(h, acc, s->dim[0], s->dim[1], s->dim[2], &mx);
+  vol_free(h, d_org), vol_free(h, d_val), vol_free(h, d_tab);
+  if (rc) return rc;
+  h->P.med.max_density = s->max_density > 0.f ? s->max_density : mx;  // VDBSceneBuilder.h:54-55: max voxel
+  if (!(h->P.med.max_density > 0.f)) return fail(h, "cvr_set_scene_sparse: the volume is empty");
+  h->scene_set = true;
+  return 0;
+}
+
+int cvr_set_scene_procedural(cvr_handle h, const char* kind_c, int32_t n, uint32_t seed, const cvr_scene_desc* s,
+                             float* max_density_out) {
+  CVR_CHECK_HANDLE(h);
+  if (!kind_c || !s) return fail(h, "cvr_set_scene_procedural: null argument");
+  const std::string kind(kind_c);
+  if (kind != "fbm" && kind != "sparsefbm") return fail(h, "cvr_set_scene_procedural: unknown kind '%s' (fbm | sparsefbm)", kind_c);
+  if (n < 8 || n > 4096) return fail(h, "cvr_set_scene_procedural: n must be in [8, 4096]");
+  if (!(s->scale > 0.f)) return fail(h, "cvr_set_scene_procedural: scale must be positive");
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_volume(h);
+  set_medium_scalars(h, s->box_min, s->box_max, s->scale, s->hg_g, s->ggx_alpha, s->ggx_eta, s->albedo_const);
+  const FbmAccessor acc{seed ? seed : 0x5eedu, kind == "sparsefbm" ? 1 : 0};
+  float mx = 0.f;
+  if (kind == "sparsefbm") {
+    if (int rc = build_bricks(h, acc, n, n, n, &mx)) return rc;
+  } else {  // dense cell8 generated in place
+    MediumParams& m = h->P.med;
+    m.dnx = m.dny = m.dnz = n;
+    m.btable = nullptr, m.bmx = m.bmy = m.bmz = 0;
+    const size_t ncell = (size_t)(n + 1) * (n + 1) * (n + 1);
+    if (ncell >= (1ull << 32)) return fail(h, "cvr_set_scene_procedural: grid too large for 32-bit cell indices");
+    CVR_CUDA(h, vol_alloc(h, (void**)&h->d_dcells, ncell * 8 * sizeof(float)));
+    const int bt = 256;
+    const int g = (int)std::min<size_t>((ncell + bt - 1) / bt, (size_t)h->sm_count * 32);
+    k_build_cells_fn<<<g, bt, 0, h->stream>>>(acc, n, n, n, (float4*)h->d_dcells);
+    CVR_CUDA(h, cudaGetLastError());
+    h->maj_dim[0] = h->maj_dim[1] = h->maj_dim[2] = (uint32_t)(n + 1 + CVR_BRICK - 1) / CVR_BRICK;
+    const size_t nbk = (size_t)h->maj_dim[0] * h->maj_dim[1] * h->maj_dim[2];
+    CVR_CUDA(h, vol_alloc(h, (void**)&h->d_majorant, nbk * sizeof(float)));
+    k_build_majorant<<<(unsigned)((nbk * 32 + bt - 1) / bt), bt, 0, h->stream>>>(
+        (const float4*)h->d_dcells, n, n, n, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2], h->d_majorant);
+    CVR_CUDA(h, cudaGetLastError());
+    // max voxel = max over the majorant grid
+    std::vector<float> maj(nbk);
+    CVR_CUDA(h, cudaMemcpyAsync(maj.data(), h->d_majorant, nbk * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (float v : maj) mx = std::max(mx, v);
+    m.dcells = h->d_dcells;
+    h->scene_layout = LAYOUT_CELL8;
+    h->volume_bytes = ncell * 32;
+    h->inited = false;
+  }
+  h->P.med.max_density = s->max_density > 0.f ? s->max_density : (mx > 0.f ? mx : 1.f);
+  if (max_density_out) *max_density_out = h->P.med.max_density;
+  h->scene_set = true;
+  return 0;
+}
+
+int cvr_get_volume_info(cvr_handle h, uint64_t* layout_bytes, uint64_t* n_bricks, int32_t* layout) {
+  CVR_CHECK_HANDLE(h);
+  if (layout_bytes) *layout_bytes = h->volume_bytes;
+  if (n_bricks) *n_bricks = h->n_bricks;
+  if (layout) *layout = h->scene_layout;
   return 0;
 }
 
@@ -1072,7 +1280,9 @@ int cvr_debug_lookup(cvr_handle h, const float* p, int n, float* dens, float* al
   CVR_CUDA(h, cudaMalloc(&d_d, (size_t)n * 4));
   CVR_CUDA(h, cudaMalloc(&d_a, (size_t)n * 12));
   CVR_CUDA(h, cudaMemcpyAsync(d_p, p, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
-  if (h->layout == LAYOUT_CELL8)
+  if (h->scene_layout == LAYOUT_BRICK)
+    k_debug_lookup<LAYOUT_BRICK><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, h->P.inv, d_p, n, d_d, d_a);
+  else if (h->scene_layout == LAYOUT_CELL8)
     k_debug_lookup<LAYOUT_CELL8><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, h->P.inv, d_p, n, d_d, d_a);
   else
     k_debug_lookup<LAYOUT_LINEAR><<<(n + 127) / 128, 128, 0, h->stream>>>(h->P.med, h->P.inv, d_p, n, d_d, d_a);

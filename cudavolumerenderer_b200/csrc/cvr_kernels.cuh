@@ -21,7 +21,11 @@
 namespace cvr {
 
 enum : int { RNG_XORWOW_PATH = 0, RNG_XORWOW_THREAD = 1, RNG_PHILOX = 2 };
-enum : int { LAYOUT_LINEAR = 0, LAYOUT_CELL8 = 1 };
+// LAYOUT_BRICK: the cell8 cells of LAYOUT_CELL8 stored SPARSELY -- bricks of 8^3 cells (16 KB),
+// only bricks that can hold a non-zero value are kept, a dense table over the brick grid maps
+// a brick coordinate to its slot (slot 0 = one shared all-zero brick).  A lookup costs one
+// extra dependent 4-byte load (the table is small enough to stay in L2).
+enum : int { LAYOUT_LINEAR = 0, LAYOUT_CELL8 = 1, LAYOUT_BRICK = 2 };
 
 struct DeviceCounters {
   unsigned long long paths, bounces, density_lookups, albedo_lookups, escaped, speculative;
@@ -106,7 +110,7 @@ CVR_DEV int code_from_normal(V3 n) {
 template <int LAYOUT>
 CVR_DEV V3 albedo_lookup(const MediumParams& m, V3 p) {
   if (m.albedo_const) return v3(m.albedo_r, m.albedo_g, m.albedo_b);
-  if (LAYOUT == LAYOUT_CELL8) return albedo_cell8(m, p);
+  if (LAYOUT != LAYOUT_LINEAR) return albedo_cell8(m, p);
   return albedo_linear(m, p);
 }
 
@@ -150,18 +154,28 @@ struct LaneCounters {
 // kernel-parameter constant bank, so they cost neither registers nor instructions.
 // density at normalised coordinate p (A7) with the invariants hoisted; same values,
 // same operation order as density_cell8 / density_linear in cvr_device.cuh
+// float offset of cell (kx,ky,kz) inside m.dcells
+template <int LAYOUT>
+CVR_DEV size_t cell_offset(const MediumParams& m, const TrackInv& I, uint32_t kx, uint32_t ky, uint32_t kz) {
+  if (LAYOUT == LAYOUT_BRICK) {
+    const uint32_t b = (kx >> 3) + m.bmx * ((ky >> 3) + m.bmy * (kz >> 3));
+    const uint32_t slot = __ldg(m.btable + b);
+    return ((size_t)slot * 512u + ((kx & 7u) | ((ky & 7u) << 3) | ((kz & 7u) << 6))) * 8u;
+  }
+  // cells < 2^32 is guaranteed by cvr_set_scene
+  return 8 * (size_t)(kx + I.sy * ky + I.sz * kz);
+}
+
 template <int LAYOUT>
 CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
-  if (LAYOUT != LAYOUT_CELL8) return density_linear(m, p);
+  if (LAYOUT == LAYOUT_LINEAR) return density_linear(m, p);
   float cx = p.x * I.rx, cy = p.y * I.ry, cz = p.z * I.rz;
   int x1 = floorf(cx), y1 = floorf(cy), z1 = floorf(cz);
   float fx = cx - x1, fy = cy - y1, fz = cz - z1;
   uint32_t kx = min((uint32_t)(x1 + 1), I.nx), ky = min((uint32_t)(y1 + 1), I.ny),
            kz = min((uint32_t)(z1 + 1), I.nz);
-  // cells < 2^32 is guaranteed by cvr_set_scene
-  uint32_t cell = kx + I.sy * ky + I.sz * kz;
   float v[8];
-  ldg256(m.dcells + 8 * (size_t)cell, v);
+  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), v);
   return trilerp<true>(v[0], v[2], v[4], v[6], v[1], v[3], v[5], v[7], fx, fy, fz);
 }
 
@@ -217,23 +231,25 @@ struct CellFetch {
   float v[8];
   float fx, fy, fz;
 };
+template <int LAYOUT>
 CVR_DEV void cell_fetch(const MediumParams& m, const TrackInv& I, float cx, float cy, float cz, CellFetch& F) {
   const float bx = __fadd_rd(cx, CVR_FLOOR_MAGIC), by = __fadd_rd(cy, CVR_FLOOR_MAGIC), bz = __fadd_rd(cz, CVR_FLOOR_MAGIC);
   // cell index k = x1 + 1, clamped like the reference's fetches (Q2: negative x1 wraps to the far edge)
   uint32_t kx = min((uint32_t)(__float_as_int(bx) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nx),
            ky = min((uint32_t)(__float_as_int(by) - (CVR_FLOOR_MAGIC_BITS - 1)), I.ny),
            kz = min((uint32_t)(__float_as_int(bz) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nz);
-  uint32_t cell = kx + I.sy * ky + I.sz * kz;
-  ldg256(m.dcells + 8 * (size_t)cell, F.v);
+  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
   F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
 }
+template <int LAYOUT>
 CVR_DEV float density_at_grid(const MediumParams& m, const TrackInv& I, float cx, float cy, float cz) {
   CellFetch F;
-  cell_fetch(m, I, cx, cy, cz, F);
+  cell_fetch<LAYOUT>(m, I, cx, cy, cz, F);
   return trilerp_fast(F.v, F.fx, F.fy, F.fz);
 }
+template <int LAYOUT>
 CVR_DEV float density_at_fast(const MediumParams& m, const TrackInv& I, V3 p) {
-  return density_at_grid(m, I, fmaf(p.x, I.rx, I.nqrx), fmaf(p.y, I.ry, I.nqry), fmaf(p.z, I.rz, I.nqrz));
+  return density_at_grid<LAYOUT>(m, I, fmaf(p.x, I.rx, I.nqrx), fmaf(p.y, I.ry, I.nqry), fmaf(p.z, I.rz, I.nqrz));
 }
 CVR_DEV float lg2_fast(float x) {  // x >= 1e-5 here: no denormal fix-up needed
   float r;
@@ -385,11 +401,11 @@ CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) 
 // ---- one Woodcock step (A6, A7): Utilities.cuh:146-152 ----
 template <int LAYOUT, bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_track_step(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C) {
-  if (FAST && LAYOUT == LAYOUT_CELL8) {
+  if (FAST && LAYOUT != LAYOUT_LINEAR) {
     float u = R.rng.next();
     R.t = fmaf(lg2_fast(fmaxf(u, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
     V3 p = v3(fmaf(R.t, R.d.x, R.o.x), fmaf(R.t, R.d.y, R.o.y), fmaf(R.t, R.d.z, R.o.z));
-    float dens = density_at_fast(P.med, I, p);
+    float dens = density_at_fast<LAYOUT>(P.med, I, p);
     if (COUNT) ++C.dens;
     bool go_on = (R.t <= R.dist);
     if (go_on) go_on = (dens * I.sig_ratio < R.rng.next());
@@ -427,13 +443,13 @@ CVR_DEV GridRay grid_ray(const TrackInv& I, const V3& o, const V3& d) {
   asm volatile("" : "+f"(G.g0x), "+f"(G.g0y), "+f"(G.g0z), "+f"(G.gdx), "+f"(G.gdy), "+f"(G.gdz));
   return G;
 }
-template <bool COUNT>
+template <int LAYOUT, bool COUNT>
 CVR_DEV void track_step_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
                              LaneCounters& C) {
   const float u = R.rng.next();
   const float u2 = R.rng.next();
   R.t = fmaf(lg2_fast(fmaxf(u, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
-  const float dens = density_at_grid(P.med, I, fmaf(R.t, G.gdx, G.g0x), fmaf(R.t, G.gdy, G.g0y),
+  const float dens = density_at_grid<LAYOUT>(P.med, I, fmaf(R.t, G.gdx, G.g0x), fmaf(R.t, G.gdy, G.g0y),
                                      fmaf(R.t, G.gdz, G.g0z));
   if (COUNT) ++C.dens;
   // select form (no divergent branch): inside ? (accepted ? event : keep tracking) : parked boundary
@@ -452,7 +468,7 @@ CVR_DEV void track_step_fast(const KernelParams& P, const TrackInv& I, const Gri
 // counted as speculative and the generator is rolled back by two draws.  The state after 2
 // draws (v2,v3,v4,n1,n2) shares three words with the state after 4 (v4,n1,n2,n3,n4), so
 // the roll-back is six selects on two saved words, not an inverse computation.
-template <bool COUNT>
+template <int LAYOUT, bool COUNT>
 CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
                              LaneCounters& C) {
   Xorwow& g = R.rng;
@@ -461,8 +477,8 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   const float t1 = fmaf(lg2_fast(fmaxf(u1, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
   const float t2 = fmaf(lg2_fast(fmaxf(u2, CVR_EPS)), I.neg_ln2_inv_sigmat, t1);
   CellFetch F1, F2;
-  cell_fetch(P.med, I, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y), fmaf(t1, G.gdz, G.g0z), F1);
-  cell_fetch(P.med, I, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y), fmaf(t2, G.gdz, G.g0z), F2);
+  cell_fetch<LAYOUT>(P.med, I, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y), fmaf(t1, G.gdz, G.g0z), F1);
+  cell_fetch<LAYOUT>(P.med, I, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y), fmaf(t2, G.gdz, G.g0z), F2);
   // both loads must be in flight before the first blend: tie the two results together so
   // that ptxas cannot consume load 1 (and reuse its registers) before load 2 is issued
   // (a REAL data dependency: an empty asm leaves nothing for ptxas to order; density values
@@ -502,7 +518,7 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
 // fewer lookups per path.  RNG consumption differs from the reference's global-majorant
 // loop, so parity of this mode is statistical.  `texit`/`mu` describe the
 // brick the path is in and are recomputed whenever texit <= t.
-template <bool COUNT, class Rng>
+template <int LAYOUT, bool COUNT, class Rng>
 CVR_DEV void do_track_step_local(const KernelParams& P, const TrackInv& I, PathRegs<Rng>& R, LaneCounters& C,
                                  float& texit, float& mu) {
   if (texit <= R.t) {
@@ -545,7 +561,7 @@ CVR_DEV void do_track_step_local(const KernelParams& P, const TrackInv& I, PathR
   }
   R.t = tn;
   V3 p = v3(fmaf(R.t, R.d.x, R.o.x), fmaf(R.t, R.d.y, R.o.y), fmaf(R.t, R.d.z, R.o.z));
-  float dens = density_at_fast(P.med, I, p);
+  float dens = density_at_fast<LAYOUT>(P.med, I, p);
   if (COUNT) ++C.dens;
   if (dens >= R.rng.next() * mu) R.state = S_SCATTER;  // real collision with probability dens / mu
 }
@@ -578,7 +594,7 @@ CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C
   else
     R.o = R.o + R.d * R.t;
   V3 albedo;
-  if (FAST && LAYOUT == LAYOUT_CELL8) {
+  if (FAST && LAYOUT != LAYOUT_LINEAR) {
     V3 ac = v3((R.o.x - P.med.box_min.x) * P.inv.aix, (R.o.y - P.med.box_min.y) * P.inv.aiy,
                (R.o.z - P.med.box_min.z) * P.inv.aiz);
     albedo = P.med.albedo_const ? v3(P.med.albedo_r, P.med.albedo_g, P.med.albedo_b) : albedo_cell8_fast(P.med, ac);
@@ -1082,7 +1098,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
     const uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
 
     // ---------------------------------------------------------------- Woodcock steps
-    if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
+    if (FAST && LAYOUT != LAYOUT_LINEAR && !LOCAL) {
       const GridRay G = grid_ray(I, R.o, R.d);
       for (int it = 0; it < P.track_steps; it += P.pair ? 2 : 1) {
         unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
@@ -1094,9 +1110,9 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
         }
         if (R.state == S_TRACK) {
           if (P.pair)
-            track_pair_fast<COUNT>(P, I, G, R, C);
+            track_pair_fast<LAYOUT, COUNT>(P, I, G, R, C);
           else
-            track_step_fast<COUNT>(P, I, G, R, C);
+            track_step_fast<LAYOUT, COUNT>(P, I, G, R, C);
         }
       }
     } else {
@@ -1113,7 +1129,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
         }
         if (have && R.state == S_TRACK) {
           if (LOCAL)
-            do_track_step_local<COUNT>(P, I, R, C, texit, mu);
+            do_track_step_local<LAYOUT, COUNT>(P, I, R, C, texit, mu);
           else
             do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
         }
@@ -1310,7 +1326,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
     // tracking paths of this warp that are NOT in this batch: worth leaving the loop early
     // for (they merge with the stragglers into a fuller batch)
     bool others_track = (key == 0 ? c0 - n : c0) != 0u;
-    if (FAST && LAYOUT == LAYOUT_CELL8 && !LOCAL) {
+    if (FAST && LAYOUT != LAYOUT_LINEAR && !LOCAL) {
       GridRay G = grid_ray(I, R.o, R.d);
       if (P.pair) {
         if (P.refill > 0 && others_track)  // top up the lanes this batch left empty
@@ -1326,14 +1342,14 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
           // few lanes left: without refill, stop if they can merge with waiting paths; with
           // refill, stop once nothing is left to refill from (the events are waiting)
           if (it > 0 && __popc(trk) < P.track_min_lanes && (others_track == (P.refill == 0))) break;
-          if (R.state == S_TRACK) track_pair_fast<COUNT>(P, I, G, R, C);
+          if (R.state == S_TRACK) track_pair_fast<LAYOUT, COUNT>(P, I, G, R, C);
         }
       } else {
         for (int it = 0; it < P.track_steps; ++it) {
           unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
           if (trk == 0) break;
           if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
-          if (R.state == S_TRACK) track_step_fast<COUNT>(P, I, G, R, C);
+          if (R.state == S_TRACK) track_step_fast<LAYOUT, COUNT>(P, I, G, R, C);
         }
       }
     } else {
@@ -1344,7 +1360,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
         if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
         if (R.state == S_TRACK) {
           if (LOCAL)
-            do_track_step_local<COUNT>(P, I, R, C, texit, mu);
+            do_track_step_local<LAYOUT, COUNT>(P, I, R, C, texit, mu);
           else
             do_track_step<LAYOUT, COUNT, FAST>(P, I, R, C);
         }

@@ -12,6 +12,7 @@
 //   "fbm"    n^3 value-noise fBm, rho = max(0, fbm-0.4)/0.6
 // Deterministic for a given seed; multithreaded over z slices.
 #include "../../include/cvr_abi.h"
+#include "cvr_noise.h"
 
 #include <algorithm>
 #include <cmath>
@@ -22,50 +23,7 @@
 
 namespace {
 
-inline uint32_t hash32(uint32_t a) {
-  a = (a + 0x7ed55d16u) + (a << 12);
-  a = (a ^ 0xc761c23cu) ^ (a >> 19);
-  a = (a + 0x165667b1u) + (a << 5);
-  a = (a + 0xd3a2646cu) ^ (a << 9);
-  a = (a + 0xfd7046c5u) + (a << 3);
-  a = (a ^ 0xb55a4f09u) ^ (a >> 16);
-  return a;
-}
-
-inline float lattice(int x, int y, int z, uint32_t octave, uint32_t seed) {
-  uint32_t key = ((uint32_t)x & 1023u) + 1024u * (((uint32_t)y & 1023u) + 1024u * ((uint32_t)z & 1023u));
-  uint32_t hv = hash32(key ^ (octave * 0x9e3779b9u) ^ seed);
-  return (float)(hv >> 8) * (1.0f / 16777216.0f);
-}
-
-inline float fade(float t) { return t * t * (3.0f - 2.0f * t); }
-
-// value noise at lattice-space position p
-inline float vnoise(float px, float py, float pz, uint32_t octave, uint32_t seed) {
-  float fx = std::floor(px), fy = std::floor(py), fz = std::floor(pz);
-  int x = (int)fx, y = (int)fy, z = (int)fz;
-  float u = fade(px - fx), v = fade(py - fy), w = fade(pz - fz);
-  float c000 = lattice(x, y, z, octave, seed), c100 = lattice(x + 1, y, z, octave, seed);
-  float c010 = lattice(x, y + 1, z, octave, seed), c110 = lattice(x + 1, y + 1, z, octave, seed);
-  float c001 = lattice(x, y, z + 1, octave, seed), c101 = lattice(x + 1, y, z + 1, octave, seed);
-  float c011 = lattice(x, y + 1, z + 1, octave, seed), c111 = lattice(x + 1, y + 1, z + 1, octave, seed);
-  float a = c000 + u * (c100 - c000), b = c010 + u * (c110 - c010);
-  float c = c001 + u * (c101 - c001), d = c011 + u * (c111 - c011);
-  float e = a + v * (b - a), f = c + v * (d - c);
-  return e + w * (f - e);
-}
-
-// 5 octaves, lacunarity 2, gain 0.5, normalised to [0,1]
-inline float fbm5(float px, float py, float pz, uint32_t seed) {
-  float sum = 0.f, amp = 0.5f, norm = 0.f;
-  for (uint32_t o = 0; o < 5; ++o) {
-    sum += amp * vnoise(px, py, pz, o, seed);
-    norm += amp;
-    px *= 2.f, py *= 2.f, pz *= 2.f;
-    amp *= 0.5f;
-  }
-  return sum / norm;
-}
+using cvrnoise::fbm5;
 
 template <class F>
 void parallel_z(int nz, F f) {
@@ -207,16 +165,15 @@ extern "C" int cvr_synth_volume(const char* kind_c, int32_t nx, int32_t ny, int3
     if (max_density) *max_density = mx;  // VDBSceneBuilder.h:54-55
     return 0;
   }
-  if (kind == "fbm") {
+  if (kind == "fbm" || kind == "sparsefbm") {
     const uint32_t sd = seed ? seed : 0x5eedu;
-    const float period = 128.f;
+    const bool sparse = kind == "sparsefbm";
     std::vector<float> zmax((size_t)nz, 0.f);
     parallel_z(nz, [&](int z) {
       float m = 0.f;
       for (int y = 0; y < ny; ++y)
         for (int x = 0; x < nx; ++x) {
-          float f = fbm5(x / period, y / period, z / period, sd);
-          float rho = std::max(0.f, f - 0.4f) / 0.6f;
+          float rho = sparse ? cvrnoise::sparsefbm_density(x, y, z, sd) : cvrnoise::fbm_density(x, y, z, sd);
           density[x + (size_t)nx * (y + (size_t)ny * z)] = rho;
           m = std::max(m, rho);
         }

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import CvrError, Counters, SceneDesc
+from .abi import CvrError, Counters, SceneDesc, SparseDesc
 
 
 class Scene:
@@ -64,6 +64,67 @@ class Scene:
     @property
     def volume_bytes(self) -> int:
         return self.density.nbytes + (self.albedo.nbytes if self.albedo is not None else 0)
+
+
+class SparseScene:
+    """A VDB-style sparse medium: 8^3 leaves re-laid into device bricks without densifying
+    (cvr_set_scene_sparse).  Same medium scalars as Scene; constant albedo."""
+
+    def __init__(self, origins: np.ndarray, values: np.ndarray, dim, bbox_min, box_min=(-0.5,) * 3, box_max=(0.5,) * 3,
+                 scale: float = 100.0, max_density: float = 0.0, fov_x: float = 0.7, albedo_const=(1.0, 1.0, 1.0),
+                 hg_g: float = 0.0, name: str = "sparse"):
+        self.origins = np.ascontiguousarray(origins, np.int32).reshape(-1, 3)
+        self.values = np.ascontiguousarray(values, np.float32).reshape(-1, 512)
+        if len(self.origins) != len(self.values):
+            raise ValueError("one origin per leaf")
+        self.dim = tuple(int(v) for v in dim)
+        self.bbox_min = tuple(int(v) for v in bbox_min)
+        self.box_min, self.box_max = tuple(map(float, box_min)), tuple(map(float, box_max))
+        self.scale, self.max_density, self.fov_x = float(scale), float(max_density), float(fov_x)
+        self.albedo_const = tuple(map(float, albedo_const))
+        self.hg_g = float(hg_g)
+        self.inv_view = None
+        self.name = name
+
+    def desc(self) -> SparseDesc:
+        d = SparseDesc()
+        d.dim[:] = self.dim
+        d.bbox_min[:] = self.bbox_min
+        d.n_leaves = len(self.origins)
+        d.leaf_origins = self.origins.ctypes.data
+        d.leaf_values = self.values.ctypes.data
+        d.albedo_const[:] = self.albedo_const
+        d.box_min[:] = self.box_min
+        d.box_max[:] = self.box_max
+        d.scale, d.max_density, d.hg_g = self.scale, self.max_density, self.hg_g
+        d.ggx_alpha[:] = (0.1, 0.1)
+        d.ggx_eta = float(np.float32(1.05) / np.float32(1.01))
+        return d
+
+
+class ProceduralScene:
+    """A volume generated on the device (cvr_set_scene_procedural): kind "fbm" (dense) or
+    "sparsefbm" (VDB-style, ~3 % of the bricks active), n^3 index space."""
+
+    def __init__(self, kind: str, n: int, seed: int = 0, box_min=(-0.5,) * 3, box_max=(0.5,) * 3, scale: float = 100.0,
+                 max_density: float = 0.0, fov_x: float = 0.7, albedo_const=(0.99,) * 3, hg_g: float = 0.0):
+        self.kind, self.n, self.seed = kind, int(n), int(seed)
+        self.box_min, self.box_max = tuple(map(float, box_min)), tuple(map(float, box_max))
+        self.scale, self.max_density, self.fov_x = float(scale), float(max_density), float(fov_x)
+        self.albedo_const = tuple(map(float, albedo_const))
+        self.hg_g = float(hg_g)
+        self.inv_view = None
+        self.name = f"{kind}{n}"
+
+    def desc(self) -> SceneDesc:
+        d = SceneDesc()
+        d.albedo_const[:] = self.albedo_const
+        d.box_min[:] = self.box_min
+        d.box_max[:] = self.box_max
+        d.scale, d.max_density, d.hg_g = self.scale, self.max_density, self.hg_g
+        d.ggx_alpha[:] = (0.1, 0.1)
+        d.ggx_eta = float(np.float32(1.05) / np.float32(1.01))
+        return d
 
 
 class VolPTKernelLauncher:
@@ -156,10 +217,23 @@ class VolPTKernelLauncher:
         self._ck(self._lib.cvr_get_iterations(self._h, C.byref(n)), "getNIterations")
         return n.value
 
-    def setScene(self, scene: Scene) -> None:
+    def setScene(self, scene) -> None:
         d = scene.desc()
-        self._ck(self._lib.cvr_set_scene(self._h, C.byref(d)), "setScene")
+        if isinstance(scene, SparseScene):
+            self._ck(self._lib.cvr_set_scene_sparse(self._h, C.byref(d)), "setScene(sparse)")
+        elif isinstance(scene, ProceduralScene):
+            mx = C.c_float()
+            self._ck(self._lib.cvr_set_scene_procedural(self._h, scene.kind.encode(), scene.n, scene.seed, C.byref(d),
+                                                        C.byref(mx)), "setScene(procedural)")
+            scene.max_density = float(mx.value)
+        else:
+            self._ck(self._lib.cvr_set_scene(self._h, C.byref(d)), "setScene")
         self._scene = scene
+
+    def volumeInfo(self) -> dict:
+        b, n, lay = C.c_uint64(), C.c_uint64(), C.c_int32()
+        self._ck(self._lib.cvr_get_volume_info(self._h, C.byref(b), C.byref(n), C.byref(lay)), "volumeInfo")
+        return {"layout_bytes": b.value, "bricks": n.value, "layout": ("linear", "cell8", "brick")[lay.value]}
 
     def getScene(self) -> Scene:
         return self._scene

@@ -57,6 +57,37 @@ def from_vdb(path: str) -> Scene:
                  name=path.rsplit("/", 1)[-1])
 
 
+def sparse_from_vdb(path: str, albedo_const=(1.0, 1.0, 1.0)):
+    """The density grid of a .vdb file as a SparseScene: its leaves go to device bricks without
+    densifying (lookups identical to from_vdb's dense grid; constant albedo)."""
+    from .launcher import SparseScene
+    from .vdb import VdbFile
+    import numpy as np
+
+    with VdbFile(path) as f:
+        g = f.grid("density")
+        org, msk, val = f.leaves("density")
+    bits = np.unpackbits(msk.view(np.uint8).reshape(len(msk), 64), axis=1, bitorder="little").astype(bool)
+    val = np.where(bits, val, np.float32(0.0))  # inactive voxels read as 0 (VDBAdapter.cpp:66)
+    return SparseScene(org, val, g["dim"], g["bbox_min"], scale=100.0, albedo_const=albedo_const,
+                       name=path.rsplit("/", 1)[-1])
+
+
+def fbm_device(n: int = 1024, seed: int = 0, albedo: float = 0.99):
+    """C4: fBm n^3 generated on the device into the dense cell8 layout (no host staging)."""
+    from .launcher import ProceduralScene
+
+    return ProceduralScene("fbm", n, seed, albedo_const=(albedo,) * 3)
+
+
+def sparse_fbm(n: int = 2048, seed: int = 0, albedo: float = 0.99):
+    """C5: VDB-style sparse n^3 volume (~3 % of the 8^3 bricks active) generated on the device
+    into the brick layout."""
+    from .launcher import ProceduralScene
+
+    return ProceduralScene("sparsefbm", n, seed, albedo_const=(albedo,) * 3)
+
+
 SCENES = {"bucky": bucky, "hetvol": hetvol, "manix": manix, "fbm": fbm}
 
 

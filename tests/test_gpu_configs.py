@@ -5,10 +5,13 @@ render completely: direct comparison.  C2 (hetvol 1024^2 x 64 spp, regenerationS
 (MANIX 1024^2 x 256 spp, 10x10 tiles) are checked through size-independent properties
 (sharding recomposition, tile/fused equivalence, untouched remainder pixels, exact path
 counts) plus an oracle comparison on a bounded sample of the same image."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+REAL_VDB = "/root/reference/data/vdb/bonsai_small.vdb"
 
 
 @pytest.fixture(scope="module")
@@ -148,3 +151,179 @@ def test_hbm_resident_volume_runs_and_matches_small_grid_statistics(cvr):
     assert abs(mg - ml) / mg <= 0.01
     assert abs(cg["bounces"] - cl["bounces"]) / cg["bounces"] <= 0.02
     assert cl["density_lookups"] < cg["density_lookups"]
+
+
+# ------------------------------------------------------------------ brick layout (sparse) and device-generated volumes
+def _same_lookups(cvr, kl_a, kl_b, n=4096, seed=1):
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(-0.15, 1.15, size=(n, 3)).astype(np.float32)  # includes the wrap / clamp edges (Q2)
+    p[:64] = rng.integers(0, 2, size=(64, 3)).astype(np.float32)  # exact corners
+    da, _ = kl_a.debugLookup(p)
+    db, _ = kl_b.debugLookup(p)
+    return np.array_equal(da, db), float(np.abs(da - db).max())
+
+
+def test_brick_layout_equals_dense_cells(cvr):
+    """The sparse brick layout stores the SAME lookup cells as the dense cell8 layout: a
+    device-generated sparse volume and the dense array of the same voxels give bit-identical
+    lookups, event counters and images."""
+    n, seed = 96, 4  # seed 4: 8 % of the 12^3 bricks of this small volume are active
+    den, _, mx = cvr.abi.synth_volume("sparsefbm", n, n, n, seed, with_albedo=False)
+    assert 0.005 < float((den > 0).mean()) < 0.5
+    dense = cvr.Scene(den, None, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=mx, albedo_const=(0.99,) * 3)
+    out = {}
+    for name, sc in (("dense", dense), ("brick", cvr.scenes.sparse_fbm(n, seed))):
+        kl = cvr.RegenerationVolPTsk(0)
+        kl.setScene(sc)
+        kl.setSeed(5)
+        img = kl.renderImage((128, 128), (1, 1), 8, fov_x=0.7)
+        out[name] = (kl, img, kl.counters(), kl.volumeInfo())
+    assert out["brick"][3]["layout"] == "brick" and out["dense"][3]["layout"] == "cell8"
+    assert 0 < out["brick"][3]["bricks"] < (n // 8 + 1) ** 3
+    assert out["brick"][3]["layout_bytes"] < out["dense"][3]["layout_bytes"]
+    same, err = _same_lookups(cvr, out["dense"][0], out["brick"][0])
+    assert same, err
+    for k in ("paths", "bounces", "density_lookups", "albedo_lookups", "escaped"):
+        assert out["dense"][2][k] == out["brick"][2][k], k
+    assert np.nanmax(np.abs(out["dense"][1] - out["brick"][1])) <= 5e-6
+    # local-majorant tracking works on bricks too and skips the empty ones
+    kl = cvr.RegenerationVolPTsk(0, tracking="local")
+    kl.setScene(cvr.scenes.sparse_fbm(n, seed))
+    kl.setSeed(5)
+    img = kl.renderImage((128, 128), (1, 1), 8, fov_x=0.7)
+    c = kl.counters()
+    assert c["density_lookups"] < 0.5 * out["brick"][2]["density_lookups"]
+    assert abs(float(np.nanmean(img[..., :3])) - float(np.nanmean(out["brick"][1][..., :3]))) <= 0.01
+    kl.close()
+    for v in out.values():
+        v[0].close()
+
+
+def test_device_generated_fbm_equals_host_generated(cvr):
+    """cvr_set_scene_procedural("fbm") builds the dense cell8 layout on the device from the same
+    noise functions the host generator uses (csrc/cvr_noise.h): identical lookups."""
+    n = 64
+    a = cvr.RegenerationVolPTsk(0)
+    a.setScene(cvr.scenes.fbm(n))
+    b = cvr.RegenerationVolPTsk(0)
+    sc = cvr.scenes.fbm_device(n)
+    b.setScene(sc)
+    assert abs(sc.max_density - cvr.scenes.fbm(n).max_density) == 0.0
+    same, err = _same_lookups(cvr, a, b)
+    assert same, err
+    a.close()
+    b.close()
+
+
+def test_vdb_leaves_to_bricks_equals_densified_grid(cvr, tmp_path):
+    """VDB leaves re-laid into device bricks WITHOUT densifying (cvr_set_scene_sparse) give the
+    lookups of the densified grid the reference builds (VDBAdapter.cpp:57-76) -- with a volume
+    origin that is not a multiple of 8, so that bricks straddle leaves."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import vdb_writer as W
+
+    rng = np.random.default_rng(4)
+    shape = (45, 38, 52)
+    d = rng.random(shape).astype(np.float32)
+    z, y, x = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    blob = ((x - 20) ** 2 + (y - 18) ** 2 + (z - 25) ** 2 < 150) | ((x - 44) ** 2 + (y - 5) ** 2 + (z - 40) ** 2 < 60)
+    d = np.where(blob, 0.2 + 0.8 * d, 0).astype(np.float32)
+    d[0, 0, 0] = d[-1, -1, -1] = 0.5  # pin the bounding box
+    path = REAL_VDB if os.path.exists(REAL_VDB) else None
+    origin = (-13, 3, 21)
+    if path is None:
+        path = str(tmp_path / "s.vdb")
+        a = np.stack([d, d, d], -1)
+        W.write_vdb(path, [("density", 1, 0.0, W.leaves_from_dense(d, d != 0, origin)),
+                           ("albedo", 3, (0, 0, 0), W.leaves_from_dense(a, d != 0, origin))])
+    dense_sc = cvr.scenes.from_vdb(path)
+    dense = cvr.Scene(dense_sc.density, None, dense_sc.box_min, dense_sc.box_max, scale=100.0,
+                      max_density=dense_sc.max_density, albedo_const=(0.9, 0.8, 0.7))
+    sparse = cvr.scenes.sparse_from_vdb(path, albedo_const=(0.9, 0.8, 0.7))
+    ka, kb = cvr.RegenerationVolPTsk(0), cvr.RegenerationVolPTsk(0)
+    ka.setScene(dense)
+    kb.setScene(sparse)
+    same, err = _same_lookups(cvr, ka, kb)
+    assert same, err
+    ka.setSeed(2), kb.setSeed(2)
+    ia = ka.renderImage((96, 96), (1, 1), 8, fov_x=0.7)
+    ib = kb.renderImage((96, 96), (1, 1), 8, fov_x=0.7)
+    ca, cb = ka.counters(), kb.counters()
+    for k in ("paths", "bounces", "density_lookups", "albedo_lookups", "escaped"):
+        assert ca[k] == cb[k], k
+    assert np.nanmax(np.abs(ia - ib)) <= 5e-6
+    assert kb.volumeInfo()["layout"] == "brick" and kb.volumeInfo()["bricks"] > 0
+    ka.close()
+    kb.close()
+
+
+def test_c4_fbm_1024_full_config(cvr):
+    """C4: fBm 1024^3 (34.5 GB of lookup cells, generated on the device), albedo 0.99,
+    2048 x 2048 x 128 spp = 5.4e8 paths in one launch; spp sharding recomposes at reduced spp."""
+    sc = cvr.scenes.fbm_device(1024)
+    kl = cvr.RegenerationVolPTsk(0)
+    kl.setScene(sc)
+    info = kl.volumeInfo()
+    assert info["layout"] == "cell8" and info["layout_bytes"] == 1025 ** 3 * 32
+    res, spp = 2048, 128
+    kl.setSeed(0)
+    img = kl.renderImage((res, res), (1, 1), spp, fov_x=sc.fov_x)
+    c = kl.counters()
+    assert c["paths"] == res * res * spp
+    assert 0.3 < float(np.nanmean(img[..., :3])) < 0.99 and c["albedo_lookups"] / c["paths"] > 3.0  # long multi-scatter paths
+    print(f"C4 fbm1024 2048^2 x {spp}: {c['paths'] / c['kernel_ms'] / 1e3:.1f} Msamples/s, "
+          f"{c['density_lookups'] / c['paths']:.1f} lookups/path, {c['bounces'] / c['paths']:.2f} bounces/path")
+    # sharding property at 512^2 x 8 spp
+    kl.resetCounters()
+    kl.setSeed(0)
+    full = kl.renderImage((512, 512), (1, 1), 8, fov_x=sc.fov_x)
+    acc = np.zeros_like(full)
+    for r in range(4):
+        kl.setSeed(0)
+        acc += kl.renderImage((512, 512), (1, 1), 8, fov_x=sc.fov_x, sample_first=2 * r, sample_count=2)
+    good = ~np.isnan(full[..., :3]) & ~np.isnan(acc[..., :3])
+    assert np.max(np.abs(acc[..., :3][good] - full[..., :3][good])) <= 2e-5
+    kl.close()
+
+
+def test_c5_sparse_2048_config(cvr):
+    """C5: sparse 2048^3 VDB-style volume in the brick layout (dense cells would be 275 GB),
+    4096 x 4096; the full 1024 spp is 1.7e10 paths (the 64-bit path counter is covered by
+    test_more_than_2_to_32_paths_in_one_launch), so the image properties are checked at 4 spp:
+    tile and sample sharding over 8 ranks recompose the single-GPU image."""
+    sc = cvr.scenes.sparse_fbm(2048)
+    kl = cvr.RegenerationVolPTsk(0)
+    kl.setScene(sc)
+    info = kl.volumeInfo()
+    assert info["layout"] == "brick" and 0.01 < info["bricks"] / 257 ** 3 < 0.25
+    assert info["layout_bytes"] < 80e9
+    res, spp = 4096, 4
+    kl.setSeed(0)
+    full = kl.renderImage((res, res), (8, 8), spp, fov_x=sc.fov_x, fuse_tiles=True)
+    c = kl.counters()
+    assert c["paths"] == res * res * spp
+    assert c["albedo_lookups"] > 0.05 * c["paths"] and float(np.nanmean(full[..., :3])) < 0.999  # the medium is hit
+    print(f"C5 sparse2048 4096^2 x {spp} (global majorant): {c['paths'] / c['kernel_ms'] / 1e3:.1f} Msamples/s, "
+          f"{c['density_lookups'] / c['paths']:.1f} lookups/path, {c['bounces'] / c['paths']:.2f} bounces/path, "
+          f"bricks {info['bricks']}, {info['layout_bytes'] / 1e9:.1f} GB")
+    img = np.zeros_like(full)
+    for r in range(8):  # tile sharding: disjoint pixels, seeds indexed by the global tile number
+        kl.setSeed(0)
+        kl.renderImage((res, res), (8, 8), spp, fov_x=sc.fov_x, host_image=img, tile_first=r, tile_stride=8, fuse_tiles=True)
+    good = ~np.isnan(full[..., :3]) & ~np.isnan(img[..., :3])
+    assert np.max(np.abs(img[..., :3][good] - full[..., :3][good])) <= 2e-5
+    kl.close()
+    # local-majorant tracking (skips the ~97 % empty bricks without a lookup): same image statistically
+    kl = cvr.RegenerationVolPTsk(0, tracking="local")
+    kl.setScene(sc)
+    kl.setSeed(0)
+    loc = kl.renderImage((res, res), (8, 8), spp, fov_x=sc.fov_x, fuse_tiles=True)
+    cl = kl.counters()
+    print(f"C5 sparse2048 4096^2 x {spp} (local majorants): {cl['paths'] / cl['kernel_ms'] / 1e3:.1f} Msamples/s, "
+          f"{cl['density_lookups'] / cl['paths']:.1f} lookups/path")
+    assert cl["density_lookups"] < 0.5 * c["density_lookups"]
+    assert abs(float(np.nanmean(loc[..., :3])) - float(np.nanmean(full[..., :3]))) <= 0.005
+    assert abs(cl["bounces"] - c["bounces"]) / c["bounces"] <= 0.02
+    kl.close()

@@ -83,7 +83,6 @@ struct KernelParams {
   int track_min_lanes;  // sorted scheduler: leave the step loop when fewer lanes are still tracking
   int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
   int pair;             // fast tracking loop: two Woodcock steps per iteration, the second speculative
-  int refill;           // warp scheduler: refill finished tracking lanes in place every n steps (0 = off)
   int policy;           // warp scheduler: 0 = fullest state wins, 1 = events first unless a full tracking batch waits
 };
 
@@ -1172,58 +1171,9 @@ inline size_t warp_sched_smem_bytes(int block, int W) {
   return (size_t)(block / 32) * (W * (sizeof(PathSlot) + 1) + 32);
 }
 
-// In-place refill of the tracking loop ("refill=n": every n Woodcock steps).  Lanes leave
-// the loop at ~13 % per step (collision or exit), so a batch that starts full is half empty
-// after five steps.  Instead of carrying the empty lanes, the finished lanes RETIRE their
-// path (dynamic part + new key) and take over a tracking-ready path of the same warp that
-// is waiting in a slot; lanes still tracking keep their registers.  Costs ~70 instructions
-// per refill against ~200 for ending the batch and forming a new one.
-// Returns the number of tracking-ready paths still waiting in slots.
-template <int K>
-CVR_DEV unsigned warp_refill(PathSlot* slots, uint8_t* keys, uint8_t* list, uint32_t (&st)[K], unsigned lane,
-                             unsigned lane_lt, bool& have, unsigned& slot, PathRegs<Xorwow>& R, uint32_t& meta_hi,
-                             const TrackInv& I, GridRay& G) {
-  const unsigned FULL = 0xffffffffu;
-  // 1. lanes whose path left the tracking state hand it back
-  if (have && R.state != S_TRACK) {
-    slot_store_dynamic(slots[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
-    keys[slot] = (uint8_t)sort_key(R.state);
-    have = false;
-    R.state = S_DONE;
-  }
-  __syncwarp();
-  // 2. owners pick up the new keys (slots that are still in a lane read back K_BUSY)
-#pragma unroll
-  for (int j = 0; j < K; ++j)
-    if (st[j] == K_BUSY) st[j] = keys[lane + 32 * j];
-  // 3. the i-th free lane takes the i-th tracking-ready slot
-  const unsigned free_m = __ballot_sync(FULL, !have);
-  const unsigned nfree = __popc(free_m);
-  unsigned base = 0;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    const bool mine = st[j] == K_TRACK;
-    const unsigned m = __ballot_sync(FULL, mine);
-    const unsigned r = base + __popc(m & lane_lt);
-    if (mine && r < nfree) {
-      list[r] = (uint8_t)(lane + 32 * j);
-      keys[lane + 32 * j] = (uint8_t)K_BUSY;
-      st[j] = K_BUSY;
-    }
-    base += __popc(m);
-  }
-  __syncwarp();
-  const unsigned ntake = min(base, nfree);
-  if (!have && (unsigned)__popc(free_m & lane_lt) < ntake) {
-    slot = list[__popc(free_m & lane_lt)];
-    slot_load_track(slots[slot], R);
-    have = true;
-    meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
-    G = grid_ray(I, R.o, R.d);
-  }
-  return base - ntake;
-}
-
+// (Measured and rejected, twice: in-place refill of finished tracking lanes from waiting
+// paths of the same warp instead of ending the batch -- hetvol 930 -> 842, bucky 4798 -> 4190
+// Msamples/s at the best refill period; profiles/r1_scheduler_evolution.md.)
 // W = path slots per warp: more slots -> fuller batches but less L1 next to the slots
 // (64: 125 KB of slots per SM at 3 CTAs, 96: 187 KB).  Measured on B200 (1024^2 x 16 spp,
 // Msamples/s, W = 64 / 96): hetvol 889 / 961, bucky 5031 / 5276 (volumes resident in L2:
@@ -1296,7 +1246,7 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
     }
     __syncwarp();
     const unsigned n = min(base, 32u);
-    bool have = lane < n;
+    const bool have = lane < n;
     unsigned slot = 0;
     PathRegs<Rng> R;
     R.state = S_DONE, R.ncode = 0, R.bounces = 0;
@@ -1320,35 +1270,26 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
     if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
     // everything the tracking loop does not touch goes back to the slot now
     if (key != 0 && have) slot_store_static(slots[slot], R);
-    uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
+    const uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
 
     // ---------------------------------------------------------------- Woodcock steps
     // tracking paths of this warp that are NOT in this batch: worth leaving the loop early
     // for (they merge with the stragglers into a fuller batch)
-    bool others_track = (key == 0 ? c0 - n : c0) != 0u;
+    const bool others_track = (key == 0 ? c0 - n : c0) != 0u;
     if (FAST && LAYOUT != LAYOUT_LINEAR && !LOCAL) {
-      GridRay G = grid_ray(I, R.o, R.d);
+      const GridRay G = grid_ray(I, R.o, R.d);
+      // few lanes left and other tracking paths of this warp waiting in slots: stop, they merge
+      const int steps = P.track_steps, min_lanes = others_track ? P.track_min_lanes : 0;
       if (P.pair) {
-        if (P.refill > 0 && others_track)  // top up the lanes this batch left empty
-          others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
-        for (int it = 0, since = 0; it < P.track_steps; it += 2, since += 2) {
-          unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
-          if (P.refill > 0 && others_track && trk != FULL && (since >= P.refill || trk == 0)) {
-            others_track = warp_refill<K>(slots, keys, list, st, lane, lane_lt, have, slot, R, meta_hi, I, G) != 0u;
-            since = 0;
-            trk = __ballot_sync(FULL, R.state == S_TRACK);
-          }
-          if (trk == 0) break;
-          // few lanes left: without refill, stop if they can merge with waiting paths; with
-          // refill, stop once nothing is left to refill from (the events are waiting)
-          if (it > 0 && __popc(trk) < P.track_min_lanes && (others_track == (P.refill == 0))) break;
+        for (int it = 0; it < steps; it += 2) {
+          const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
+          if (trk == 0 || (it > 0 && __popc(trk) < min_lanes)) break;
           if (R.state == S_TRACK) track_pair_fast<LAYOUT, COUNT>(P, I, G, R, C);
         }
       } else {
-        for (int it = 0; it < P.track_steps; ++it) {
-          unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
-          if (trk == 0) break;
-          if (it > 0 && others_track && __popc(trk) < P.track_min_lanes) break;
+        for (int it = 0; it < steps; ++it) {
+          const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+          if (trk == 0 || (it > 0 && __popc(trk) < min_lanes)) break;
           if (R.state == S_TRACK) track_step_fast<LAYOUT, COUNT>(P, I, G, R, C);
         }
       }

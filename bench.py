@@ -312,7 +312,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 128)  # density + albedo cell8 layouts
     gather_peak = kl.gatherRoofline(footprint, 512, 8)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_volpt", "peak_source": peak_src,
+                "traffic": traffic,
+                "kernel": {"warp": "k_volpt_warp", "queued": "k_volpt_queued", "sorted": "k_volpt_sorted"}.get(kl.getOption("sched"), "k_volpt"),
+                "peak_source": peak_src,
                 "kernel_ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
                 "density_lookups_per_s": ctr["density_lookups"] / (ctr["kernel_ms"] * 1e-3),
                 "kernel_share_of_step": ctr["kernel_ms"] / ms,
@@ -337,7 +339,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "config": {"workload": WORKLOAD, "resolution": [RES, RES], "spp_per_gpu": SPP, "total_spp": total_spp,
                    "kernel": "regenerationSK", "rng": kl.getOption("rng"), "layout": kl.getOption("layout"),
                    "sched": kl.getOption("sched"), "arithmetic": "fused (exact=0)" if kl.getOption("exact") == "0" else "reference order (exact=1)",
-                   "tracking": kl.getOption("tracking"),
+                   "tracking": kl.getOption("tracking"), "warp_slots": kl.getOption("warp_slots"),
+                   "speculative_pair_step": kl.getOption("pair"),
                    "sharding": "spp" if world > 1 else "none", "l2": "flushed between steps (256 MiB write)",
                    "image_mean": img_mean, "nan_pixels": nan_px},
         "clocks": clk.summary(),

@@ -80,6 +80,8 @@ struct cvr_renderer {
   float4* d_acells = nullptr;
   float* d_majorant = nullptr;
   uint32_t maj_dim[3] = {0, 0, 0};
+  float* d_majorant2 = nullptr;  // second level: max over 8^3 bricks
+  uint32_t maj2_dim[3] = {0, 0, 0};
   uint32_t* d_btable = nullptr;  // brick layout: slot table over the brick grid
   uint64_t n_bricks = 0;         // brick layout: stored bricks (without the zero brick)
   unsigned long long* d_head = nullptr;
@@ -232,6 +234,8 @@ void free_volume(cvr_handle h) {
   vol_free(h, h->d_albedo);
   vol_free(h, h->d_acells);
   vol_free(h, h->d_majorant);
+  vol_free(h, h->d_majorant2);
+  h->d_majorant2 = nullptr;
   vol_free(h, h->d_btable);
   h->d_majorant = nullptr;
   h->d_btable = nullptr;
@@ -319,6 +323,20 @@ void fill_track_inv(KernelParams& P) {
 void fill_majorant(cvr_handle h) {
   h->P.inv.majorant = h->d_majorant;
   h->P.inv.mx = h->maj_dim[0], h->P.inv.my = h->maj_dim[1], h->P.inv.mz = h->maj_dim[2];
+  h->P.inv.majorant2 = h->d_majorant2;
+  h->P.inv.m2x = h->maj2_dim[0], h->P.inv.m2y = h->maj2_dim[1], h->P.inv.m2z = h->maj2_dim[2];
+}
+
+// second majorant level from the brick majorants (h->d_majorant, h->maj_dim)
+int build_majorant2(cvr_handle h) {
+  for (int a = 0; a < 3; ++a) h->maj2_dim[a] = (h->maj_dim[a] + 7) / 8;
+  const size_t n2 = (size_t)h->maj2_dim[0] * h->maj2_dim[1] * h->maj2_dim[2];
+  CVR_CUDA(h, vol_alloc(h, (void**)&h->d_majorant2, n2 * sizeof(float)));
+  k_build_majorant2<<<(unsigned)((n2 + 127) / 128), 128, 0, h->stream>>>(h->d_majorant, h->maj_dim[0], h->maj_dim[1],
+                                                                        h->maj_dim[2], h->d_majorant2, h->maj2_dim[0],
+                                                                        h->maj2_dim[1], h->maj2_dim[2]);
+  CVR_CUDA(h, cudaGetLastError());
+  return 0;
 }
 
 // fills the per-launch part of the kernel parameters and launches
@@ -679,6 +697,7 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     k_build_majorant<<<(unsigned)((n_bricks * 32 + bt - 1) / bt), bt, 0, h->stream>>>(
         (const float4*)h->d_dcells, m.dnx, m.dny, m.dnz, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2], h->d_majorant);
     CVR_CUDA(h, cudaGetLastError());
+    if (build_majorant2(h)) return 1;
   }
   m.albedo_const = s->albedo ? 0 : 1;
   m.albedo_r = s->albedo_const[0], m.albedo_g = s->albedo_const[1], m.albedo_b = s->albedo_const[2];
@@ -774,6 +793,7 @@ int build_bricks(cvr_handle h, const Acc& acc, int nx, int ny, int nz, float* ma
   k_brick_majorant<<<(unsigned)((nb * 32 + bt - 1) / bt), bt, 0, h->stream>>>(h->d_btable, (const float4*)h->d_dcells, nb,
                                                                                 h->d_majorant, d_counter + 1);
   CVR_CUDA(h, cudaGetLastError());
+  if (build_majorant2(h)) return 1;
   uint32_t max_bits = 0;
   CVR_CUDA(h, cudaMemcpyAsync(&max_bits, d_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CVR_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -864,6 +884,7 @@ int cvr_set_scene_procedural(cvr_handle h, const char* kind_c, int32_t n, uint32
     k_build_majorant<<<(unsigned)((nbk * 32 + bt - 1) / bt), bt, 0, h->stream>>>(
         (const float4*)h->d_dcells, n, n, n, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2], h->d_majorant);
     CVR_CUDA(h, cudaGetLastError());
+    if (build_majorant2(h)) return 1;
     // max voxel = max over the majorant grid
     std::vector<float> maj(nbk);
     CVR_CUDA(h, cudaMemcpyAsync(maj.data(), h->d_majorant, nbk * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -45,6 +45,9 @@ struct TrackInv {
   // local-majorant tracking ("tracking=local"): max density per brick of CVR_BRICK^3 cells
   const float* __restrict__ majorant;
   uint32_t mx, my, mz;     // brick-grid dims = ceil((n + 1) / CVR_BRICK)
+  // second majorant level: max over 8^3 bricks = 64^3 cells (empty space is crossed in 64-cell strides)
+  const float* __restrict__ majorant2;
+  uint32_t m2x, m2y, m2z;
 };
 
 #ifndef CVR_BRICK_LOG2
@@ -526,23 +529,32 @@ CVR_DEV void do_track_step_local(const KernelParams& P, const TrackInv& I, PathR
     const float g0x = fmaf(R.o.x, I.rx, I.nqrx), g0y = fmaf(R.o.y, I.ry, I.nqry), g0z = fmaf(R.o.z, I.rz, I.nqrz);
     const float tp = R.t + 1e-6f + 1e-6f * fabsf(R.t);  // probe just inside the next brick
     const float gx = fmaf(tp, gdx, g0x), gy = fmaf(tp, gdy, g0y), gz = fmaf(tp, gdz, g0z);
-    const float inv_b = 1.0f / CVR_BRICK;
+    // lookup cell of the probe point, clamped like the lookup itself (out-of-range coordinates
+    // use the far-edge cell, Q2)
+    const uint32_t kx = min((uint32_t)((int)floorf(gx) + 1), I.nx), ky = min((uint32_t)((int)floorf(gy) + 1), I.ny),
+                   kz = min((uint32_t)((int)floorf(gz) + 1), I.nz);
+    // two-level majorant mip: an empty 64^3 super-brick is crossed in one stride, otherwise
+    // the 8^3 brick the point is in
+    const uint32_t b2 = (kx >> (CVR_BRICK_LOG2 + 3)) +
+                        I.m2x * ((ky >> (CVR_BRICK_LOG2 + 3)) + I.m2y * (kz >> (CVR_BRICK_LOG2 + 3)));
+    // both levels are fetched together: the walk is a chain of dependent loads, a second
+    // round trip per brick would double its latency
+    const uint32_t b1 = (kx >> CVR_BRICK_LOG2) + I.mx * ((ky >> CVR_BRICK_LOG2) + I.my * (kz >> CVR_BRICK_LOG2));
+    const float mu2 = __ldg(I.majorant2 + b2), mu1 = __ldg(I.majorant + b1);
+    const bool coarse_empty = !(mu2 > 0.f);
+    const float size = coarse_empty ? (float)(CVR_BRICK * 8) : (float)CVR_BRICK;
+    const float inv_b = coarse_empty ? 1.0f / (CVR_BRICK * 8) : 1.0f / CVR_BRICK;
     const float jx = floorf((gx + 1.0f) * inv_b), jy = floorf((gy + 1.0f) * inv_b), jz = floorf((gz + 1.0f) * inv_b);
-    // exit parameter of this brick along the ray
-    const float bx = (gdx > 0.f ? jx + 1.0f : jx) * CVR_BRICK - 1.0f;
-    const float by = (gdy > 0.f ? jy + 1.0f : jy) * CVR_BRICK - 1.0f;
-    const float bz = (gdz > 0.f ? jz + 1.0f : jz) * CVR_BRICK - 1.0f;
+    // exit parameter of this (super-)brick along the ray
+    const float bx = (gdx > 0.f ? jx + 1.0f : jx) * size - 1.0f;
+    const float by = (gdy > 0.f ? jy + 1.0f : jy) * size - 1.0f;
+    const float bz = (gdz > 0.f ? jz + 1.0f : jz) * size - 1.0f;
     const float big = 3.0e38f;
     float ex = gdx != 0.f ? __fdividef(bx - g0x, gdx) : big;
     float ey = gdy != 0.f ? __fdividef(by - g0y, gdy) : big;
     float ez = gdz != 0.f ? __fdividef(bz - g0z, gdz) : big;
     texit = fmaxf(fminf(fminf(ex, ey), ez), tp);  // always makes progress
-    // majorant of the brick that holds the lookup CELL of the probe point (same clamping
-    // as the lookup: out-of-range coordinates use the far-edge cell, Q2)
-    uint32_t kx = min((uint32_t)((int)floorf(gx) + 1), I.nx), ky = min((uint32_t)((int)floorf(gy) + 1), I.ny),
-             kz = min((uint32_t)((int)floorf(gz) + 1), I.nz);
-    uint32_t b = (kx >> CVR_BRICK_LOG2) + I.mx * ((ky >> CVR_BRICK_LOG2) + I.my * (kz >> CVR_BRICK_LOG2));
-    mu = __ldg(I.majorant + b);
+    mu = coarse_empty ? 0.f : mu1;
   }
   const bool last = texit >= R.dist;  // this brick reaches the end of the segment
   const float tend = last ? R.dist : texit;
@@ -1391,6 +1403,19 @@ __global__ void k_build_majorant(const float4* __restrict__ cells, int nx, int n
   }
   for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
   if (lane == 0) maj[warp] = m;
+}
+
+// second majorant level: max over 8^3 bricks
+__global__ void k_build_majorant2(const float* __restrict__ maj, uint32_t mx, uint32_t my, uint32_t mz,
+                                  float* __restrict__ maj2, uint32_t m2x, uint32_t m2y, uint32_t m2z) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m2x * m2y * m2z) return;
+  const uint32_t cx = i % m2x, cy = (i / m2x) % m2y, cz = i / (m2x * m2y);
+  float m = 0.f;
+  for (uint32_t z = 8 * cz; z < min(8 * cz + 8, mz); ++z)
+    for (uint32_t y = 8 * cy; y < min(8 * cy + 8, my); ++y)
+      for (uint32_t x = 8 * cx; x < min(8 * cx + 8, mx); ++x) m = fmaxf(m, maj[x + (size_t)mx * (y + (size_t)my * z)]);
+  maj2[i] = m;
 }
 
 // ---------------------------------------------------------------- resolve (A16)

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -33,6 +34,7 @@ struct Options {
   int device = 0;
   bool dump_scene = false;  // print the loaded scene and exit (no GPU needed)
   std::string dump_raw;     // also write the float4 image as raw little-endian floats
+  bool png = false;         // also write <output>.png (Image::savePNG, Image.cpp:35-56)
   std::vector<std::pair<std::string, std::string>> lib_options;
 };
 
@@ -92,6 +94,8 @@ bool parse(int argc, char** argv, Options& o) {
       o.dump_scene = true;
     else if (a == "--dump-raw")
       o.dump_raw = need(i);
+    else if (a == "--png")
+      o.png = true;
     else if (a == "--option") {
       std::string kv = need(i);
       size_t eq = kv.find('=');
@@ -138,6 +142,52 @@ void saveHDR(const std::string& base, const float* rgba, int w, int h) {
   std::cout << "Saved " << fn << ".\n";
 }
 
+// Image::savePNG (Image.cpp:35-56): clamp to [0,1], x255, truncate, 8-bit RGB.  Written with
+// zlib directly (stored PNG chunks: signature, IHDR, one IDAT, IEND); no stb.
+void savePNG(const std::string& base, const float* rgba, int w, int h) {
+  std::vector<unsigned char> raw((size_t)h * (3 * (size_t)w + 1));
+  for (int y = 0; y < h; ++y) {
+    unsigned char* row = &raw[(size_t)y * (3 * (size_t)w + 1)];
+    row[0] = 0;  // filter type: none
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 3; ++c) {
+        float v = rgba[4 * ((size_t)y * w + x) + c];
+        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);  // NaN pixels (reference quirk) become 0
+        if (!(v == v)) v = 0.f;
+        row[1 + 3 * x + c] = (unsigned char)(v * 255.f);
+      }
+  }
+  uLongf zlen = compressBound((uLong)raw.size());
+  std::vector<unsigned char> z(zlen);
+  if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) throw std::runtime_error("png: deflate failed");
+  std::string fn = base + ".png";
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot write " + fn);
+  auto be32 = [](unsigned char* p, uint32_t v) { p[0] = v >> 24, p[1] = v >> 16, p[2] = v >> 8, p[3] = v; };
+  auto chunk = [&](const char* type, const unsigned char* data, uint32_t n) {
+    unsigned char hdr[8];
+    be32(hdr, n);
+    memcpy(hdr + 4, type, 4);
+    fwrite(hdr, 1, 8, f);
+    if (n) fwrite(data, 1, n, f);
+    uLong c = crc32(0L, hdr + 4, 4);
+    if (n) c = crc32(c, data, n);
+    unsigned char crc[4];
+    be32(crc, (uint32_t)c);
+    fwrite(crc, 1, 4, f);
+  };
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  fwrite(sig, 1, 8, f);
+  unsigned char ihdr[13];
+  be32(ihdr, (uint32_t)w), be32(ihdr + 4, (uint32_t)h);
+  ihdr[8] = 8, ihdr[9] = 2, ihdr[10] = 0, ihdr[11] = 0, ihdr[12] = 0;  // 8-bit, colour type 2 (RGB)
+  chunk("IHDR", ihdr, 13);
+  chunk("IDAT", z.data(), (uint32_t)zlen);
+  chunk("IEND", nullptr, 0);
+  fclose(f);
+  std::cout << "Saved " << fn << ".\n";
+}
+
 int runTest(const Options& o, const Scene& scene) {
   TilingConfig tiling({o.resolution[0], o.resolution[1]}, {o.n_tiles[0], o.n_tiles[1]});
   std::vector<float> times;
@@ -162,6 +212,10 @@ int runTest(const Options& o, const Scene& scene) {
         for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
       if (auto* r = dynamic_cast<CudaVolPath<StreamingVolPTsk>*>(renderer.get()))
         for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
+      if (auto* r = dynamic_cast<CudaVolPath<StreamingVolPTmk>*>(renderer.get()))
+        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
+      if (auto* r = dynamic_cast<CudaVolPath<SortingVolPTsk>*>(renderer.get()))
+        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
     }
     auto t1 = std::chrono::steady_clock::now();
     printf("initialization time : %.2f sec \n", std::chrono::duration<float>(t1 - t0).count());
@@ -183,6 +237,7 @@ int runTest(const Options& o, const Scene& scene) {
       fclose(f);
     }
     saveHDR(out_name, copy.data(), (int)o.resolution[0], (int)o.resolution[1]);
+    if (o.png) savePNG(out_name, copy.data(), (int)o.resolution[0], (int)o.resolution[1]);
     renderer.reset();
     cudaFreeHost(pixels);
   }

@@ -48,7 +48,7 @@ struct cvr_renderer {
   int exact = 0;  // 0 = fused arithmetic (queued scheduler only), 1 = the reference's operation order
   int rr = 1;
   uint32_t max_bounces = 1u << 20;
-  int block = CVR_BLOCK;
+  int block = 0;  // 0 = the selected kernel's launch-bounds block (CVR_WBLOCK for sched=warp, else CVR_BLOCK)
   int blocks_per_sm = 0;  // 0 = occupancy query
   int loop_threshold = 16;
   int counters = 1;
@@ -59,8 +59,8 @@ struct cvr_renderer {
   int warp_slots = 0;     // warp scheduler: path slots per warp (64 | 96), 0 = auto
   size_t volume_bytes = 0;  // device footprint of the density + albedo lookup layouts
   int l2_bytes = 0;
-  int track_steps = 8;
-  int track_min_lanes = 8;
+  int track_steps = 12;
+  int track_min_lanes = 12;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
   int fix_nan = 0;
 
@@ -269,6 +269,11 @@ int effective_wslots(cvr_handle h) {
 // 1026 / 1050, sparse 2048^3 1612 / 2058 -- on by default, also for HBM-resident volumes.
 int effective_pair(cvr_handle h) { return h->pair >= 0 ? h->pair : 1; }
 
+int effective_block(cvr_handle h) {
+  const int cap = h->sched == 3 ? CVR_WBLOCK : CVR_BLOCK;
+  return (h->block > 0 && h->block <= cap) ? h->block : cap;
+}
+
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
   kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h));
@@ -279,12 +284,12 @@ int ensure_init(cvr_handle h) {
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
   // the warp-private scheduler keeps its path slots in DYNAMIC shared memory (may exceed 48 KB)
-  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(h->block, effective_wslots(h)) : 0;
+  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(effective_block(h), effective_wslots(h)) : 0;
   if (h->smem_bytes)
     CVR_CUDA(h, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int per_sm = 0;
-  CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, h->block, h->smem_bytes));
-  if (per_sm < 1) return fail(h, "kernel does not fit an SM at block size %d", h->block);
+  CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, effective_block(h), h->smem_bytes));
+  if (per_sm < 1) return fail(h, "kernel does not fit an SM at block size %d", effective_block(h));
   if (h->blocks_per_sm > 0 && h->blocks_per_sm < per_sm) per_sm = h->blocks_per_sm;
   h->grid = per_sm * h->sm_count;
   h->inited = true;
@@ -383,7 +388,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
   CVR_CUDA(h, cudaEventRecord(e0, h->stream));
-  k<<<h->grid, h->block, h->smem_bytes, h->stream>>>(P);
+  k<<<h->grid, effective_block(h), h->smem_bytes, h->stream>>>(P);
   CVR_CUDA(h, cudaGetLastError());
   CVR_CUDA(h, cudaEventRecord(e1, h->stream));
   h->timing.emplace_back(e0, e1);
@@ -616,7 +621,7 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
   else if (k == "max_bounces")
     v = std::to_string(h->max_bounces);
   else if (k == "block")
-    v = std::to_string(h->block);
+    v = std::to_string(effective_block(h));
   else if (k == "blocks_per_sm")
     v = std::to_string(h->blocks_per_sm);
   else if (k == "loop_threshold")
@@ -1055,7 +1060,7 @@ int cvr_get_launch_shape(cvr_handle h, int* grid, int* block, int* regs) {
   CVR_CHECK_HANDLE(h);
   if (set_device(h) || ensure_init(h)) return 1;
   if (grid) *grid = h->grid;
-  if (block) *block = h->block;
+  if (block) *block = effective_block(h);
   if (regs) *regs = h->regs;
   return 0;
 }

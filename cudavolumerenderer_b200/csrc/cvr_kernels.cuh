@@ -1173,8 +1173,15 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 // Each path's own operation and RNG order is unchanged, so results are identical to the
 // other schedulers (event counters bit-identical, images up to fp32 atomic order).
 // =============================================================================
+// CTA shape of the warp scheduler: warps never interact, so the CTA size only sets the
+// register budget granularity.  128 threads x 7 CTAs/SM = 28 warps at 72 registers (no spills)
+// against 256 x 3 = 24 warps at 80: hetvol +2.4 %, manix +6.6 %, bucky +6.0 %, fbm 512^3 +0.6 %;
+// 128 x 8 (64 registers, spills) -12 %.
+#ifndef CVR_WBLOCK
+#define CVR_WBLOCK 128
+#endif
 #ifndef CVR_WMIN_BLOCKS
-#define CVR_WMIN_BLOCKS 3
+#define CVR_WMIN_BLOCKS 7
 #endif
 enum : uint32_t { K_TRACK = 0, K_SCATTER = 1, K_BOUNDARY = 2, K_IDLE = 3, K_DONE = 4, K_BUSY = 5 };
 
@@ -1187,11 +1194,11 @@ inline size_t warp_sched_smem_bytes(int block, int W) {
 // paths of the same warp instead of ending the batch -- hetvol 930 -> 842, bucky 4798 -> 4190
 // Msamples/s at the best refill period; profiles/r1_scheduler_evolution.md.)
 // W = path slots per warp: more slots -> fuller batches but less L1 next to the slots
-// (64: 125 KB of slots per SM at 3 CTAs, 96: 187 KB).  Measured on B200 (1024^2 x 16 spp,
+// (64: 145 KB of slots per SM at 28 warps, 96: 218 KB).  Measured on B200 (1024^2 x 16 spp,
 // Msamples/s, W = 64 / 96): hetvol 889 / 961, bucky 5031 / 5276 (volumes resident in L2:
 // fill wins), manix 2355 / 2102, fbm 512^3 1059 / 1031 (volumes beyond L2: L1 wins).
 template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64>
-__global__ void __launch_bounds__(CVR_BLOCK, CVR_WMIN_BLOCKS)
+__global__ void __launch_bounds__(CVR_WBLOCK, CVR_WMIN_BLOCKS)
     k_volpt_warp(const __grid_constant__ KernelParams P) {
   typedef Xorwow Rng;
   constexpr int K = W / 32;

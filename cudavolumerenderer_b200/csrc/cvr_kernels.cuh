@@ -1,20 +1,23 @@
 // cvr_kernels.cuh -- the sm_100a path kernels.
 //
-// One persistent-thread kernel template replaces the reference's naiveSK /
-// regenerationSK(thread) / streamingSK kernels (NaiveVolPTsk_kernel.cuh:17-87,
-// RegenerationVolPTsk_kernel.cuh:146-232, StreamingVolPTsk_kernel.cuh:219-290):
-// the kernel NAME selects the reference SEMANTICS (scatter pull-back, seed
-// advance, roulette-after-escape), the scheduling is always the B200 one:
+// Persistent-thread kernels replace the reference's naiveSK / regenerationSK(thread) /
+// streamingSK / streamingMK / sortingSK kernels (NaiveVolPTsk_kernel.cuh:17-87,
+// RegenerationVolPTsk_kernel.cuh:146-232, StreamingVolPTsk_kernel.cuh:219-290, ...): the kernel
+// NAME selects the reference SEMANTICS (scatter pull-back, seed advance, roulette-after-escape),
+// the scheduling is always this library's.  Four schedulers share the estimator blocks below
+// (do_isect, do_track_step / track_pair_fast, do_scatter, do_boundary, do_roulette):
 //
-//  * grid = SMs x resident CTAs, every warp loops until the path queue is empty;
-//  * idle lanes claim path ids with ONE warp-aggregated 64-bit atomic
-//    (ballot + popc + shuffle), consecutive ids -> consecutive pixels;
-//  * a per-lane state machine splits each bounce into {intersect, Woodcock steps,
-//    event}; the Woodcock loop runs warp-wide ("while-while") and yields to the
-//    event phase once `loop_threshold` lanes are waiting, so a lane's RNG draw
-//    order is exactly the reference's while divergence is bounded;
-//  * density lookups read one 32-byte cell (8 trilinear corners) with a single
-//    256-bit load; albedo cells are one 128-byte line.
+//  * k_volpt_warp    (default) warp-private wavefront: every warp owns 64/96 path slots in shared
+//                    memory and runs batches of <= 32 paths in the SAME state; no atomics;
+//  * k_volpt_queued  per-state ring-buffer queues per CTA (the first-round product kernel);
+//  * k_volpt_sorted  block-wide counting sort per round;
+//  * k_volpt         a lane keeps its path in registers ("while-while" with a yield threshold).
+//
+// Common to all: grid = SMs x resident CTAs, warps loop until the 64-bit path counter is
+// exhausted; idle lanes claim path ids with ONE warp-aggregated atomic (ballot + popc +
+// shuffle), consecutive ids -> consecutive pixels; a density lookup reads one 32-byte cell
+// (8 trilinear corners) with a single 256-bit load, an albedo lookup one 128-byte line; a
+// path's own operation order and RNG draw order never depend on the scheduler.
 #pragma once
 #include "cvr_device.cuh"
 

@@ -59,7 +59,7 @@ struct cvr_renderer {
   int warp_slots = 0;     // warp scheduler: path slots per warp (64 | 96), 0 = auto
   size_t volume_bytes = 0;  // device footprint of the density + albedo lookup layouts
   int l2_bytes = 0;
-  int track_steps = 12;
+  int track_steps = 16;
   int track_min_lanes = 12;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
   int fix_nan = 0;
@@ -243,6 +243,16 @@ void free_volume(cvr_handle h) {
   h->d_density = h->d_dcells = nullptr;
   h->d_albedo = h->d_acells = nullptr;
   h->scene_set = false;
+  // a multi-GB volume must not stay parked in the pool (other allocators of the process --
+  // torch, the caller's cudaMalloc -- cannot see it): give everything above 1 GiB back
+  cudaMemPool_t pool;
+  unsigned long long reserved = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+      reserved > (1ull << 30)) {
+    cudaStreamSynchronize(h->stream);
+    cudaMemPoolTrimTo(pool, 1ull << 30);
+  }
 }
 
 int ensure_allocated(cvr_handle h) {

@@ -151,7 +151,7 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
-def ref_gpu_baseline(sc, spp: int):
+def ref_gpu_baseline(sc, spp: int, ours_rgb=None):
     """The reference's OWN regenerationSK(thread) kernel compiled from its headers for
     sm_100a (oracle/_ref/libcvr_ref_gpu.so), same scene / resolution: context number."""
     import ctypes as C
@@ -175,15 +175,32 @@ def ref_gpu_baseline(sc, spp: int):
         if R.refgpu_set_camera((C.c_float * 12)(*iv.tolist()), (C.c_float * 2)(*rtv.tolist()), RES, RES,
                                C.c_float(RES), C.c_float(RES), 0, 0):
             return None
+        import numpy as np
+
         best = None
         ms, g, b = C.c_float(), C.c_int(), C.c_int()
+        imgs = []
         for i in range(3):
-            if R.refgpu_render(1, spp, 1000 + i, None, C.byref(ms), C.byref(g), C.byref(b)):
+            out = np.zeros((RES, RES, 4), np.float32)
+            if R.refgpu_render(1, spp, 1000 + i, out.ctypes.data_as(C.c_void_p), C.byref(ms), C.byref(g), C.byref(b)):
                 return None
             best = ms.value if best is None else min(best, ms.value)
+            imgs.append(out[..., :3] / spp)
         R.refgpu_release()
-        return {"kernel": "reference regenerationSK(thread) recompiled for sm_100a", "ms": best,
-                "value": RES * RES * spp / best / 1e3, "unit": METRIC, "grid": g.value, "block": b.value}
+        res = {"kernel": "reference regenerationSK(thread) recompiled for sm_100a", "ms": best,
+               "value": RES * RES * spp / best / 1e3, "unit": METRIC, "grid": g.value, "block": b.value}
+
+        def rel_rmse(a, r):  # BASELINE "RMSE vs ref": sqrt(mean((I-R)^2)) / mean(R) over RGB, NaN pixels left out
+            ok = ~(np.isnan(a).any(axis=-1) | np.isnan(r).any(axis=-1))
+            return float(np.sqrt(np.mean((a[ok] - r[ok]) ** 2)) / np.mean(r[ok]))
+
+        if ours_rgb is not None:
+            # images at matched spp from independent streams: agreement = the same relative RMSE as
+            # two runs of the reference kernel against each other (pure Monte-Carlo noise)
+            res["rmse_vs_ref"] = {"spp": spp, "ours_vs_reference": rel_rmse(ours_rgb, imgs[0]),
+                                  "reference_vs_reference": rel_rmse(imgs[1], imgs[0]),
+                                  "mean_ours": float(np.nanmean(ours_rgb)), "mean_reference": float(np.nanmean(imgs[0]))}
+        return res
     except Exception as e:  # context number only
         return {"error": str(e)}
 
@@ -330,7 +347,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         v, cores, dt, _ = cpu_sample(sc, 8)
         cpu = {"value": v, "unit": METRIC, "cores": cores, "kind": "port",
                "sample": f"{RES}x{RES} at 8 spp ({dt:.1f} s), oracle/cvr_oracle.c regenerationSK path loop"}
-        ref_gpu = ref_gpu_baseline(sc, SPP)
+        ref_gpu = ref_gpu_baseline(sc, SPP, rgb.float().cpu().numpy())
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,

@@ -296,8 +296,12 @@ CVR_DEV V3 albedo_cell8_fast(const MediumParams& m, V3 p) {
   return v3(trilerp_fast(r, fx, fy, fz), trilerp_fast(g, fx, fy, fz), trilerp_fast(b, fx, fy, fz));
 #endif
 }
-CVR_DEV bool box_intersect_fast(const V3& bmin, const V3& bmax, const V3& o, const V3& d, float& dist,
-                                V3& normal, bool& inside) {
+// Same test, but the hit face comes out as the 0..5 normal code the slots store (0:+x 1:+y 2:+z
+// 3:-x 4:-y 5:-z) and `inside` from the sign of that one direction component, instead of a
+// float3 normal, a dot product and a second compare chain.  No face matched (NaN): code 5,
+// inside false -- what code_from_normal / dot give for the zero normal.
+CVR_DEV bool box_intersect_code(const V3& bmin, const V3& bmax, const V3& o, const V3& d, float& dist, int& code,
+                                bool& inside) {
   V3 inv_r = v3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
   V3 tbot = inv_r * (bmin - o);
   V3 ttop = inv_r * (bmax - o);
@@ -306,19 +310,11 @@ CVR_DEV bool box_intersect_fast(const V3& bmin, const V3& bmax, const V3& o, con
   float largest_tmin = fmaxf(fmaxf(tmin.x, tmin.y), fmaxf(tmin.x, tmin.z));
   float smallest_tmax = fminf(fminf(tmax.x, tmax.y), fminf(tmax.x, tmax.z));
   dist = (largest_tmin > CVR_EPS) ? largest_tmin : smallest_tmax;
-  if (dist == ttop.x)
-    normal = v3(1, 0, 0);
-  else if (dist == ttop.y)
-    normal = v3(0, 1, 0);
-  else if (dist == ttop.z)
-    normal = v3(0, 0, 1);
-  else if (dist == tbot.x)
-    normal = v3(-1, 0, 0);
-  else if (dist == tbot.y)
-    normal = v3(0, -1, 0);
-  else if (dist == tbot.z)
-    normal = v3(0, 0, -1);
-  inside = dot(normal, d) > 0;
+  // Geometry.h:76-87: first match in the order top x, y, z, bottom x, y, z
+  code = dist == ttop.x ? 0 : dist == ttop.y ? 1 : dist == ttop.z ? 2 : dist == tbot.x ? 3 : dist == tbot.y ? 4 : 5;
+  const bool matched = code < 5 || dist == tbot.z;
+  const float dn = code == 0 ? d.x : code == 1 ? d.y : code == 2 ? d.z : code == 3 ? -d.x : code == 4 ? -d.y : -d.z;
+  inside = matched && dn > 0.f;  // dot(normal, d) > 0
   return (smallest_tmax > largest_tmin) && (dist > 0);
 }
 CVR_DEV V3 hg_sample_fast(V3 dir, float g, float e1, float e2) {
@@ -373,10 +369,15 @@ CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned lo
 template <bool COUNT, bool FAST = false, class Rng>
 CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
   if (COUNT) ++C.bounces;
-  V3 normal = v3(0, 0, 0);
-  bool inside;
-  const bool hit = FAST ? box_intersect_fast(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside)
-                        : box_intersect(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside);
+  bool inside, hit;
+  int ncode;
+  if (FAST) {
+    hit = box_intersect_code(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, ncode, inside);
+  } else {
+    V3 normal = v3(0, 0, 0);
+    hit = box_intersect(P.med.box_min, P.med.box_max, R.o, R.d, R.dist, normal, inside);
+    ncode = code_from_normal(normal);
+  }
   if (!hit) {
     // escaped: throughput * Le, Le == 1 (Medium.h:174-177)
     float rx = R.thr_x * 1.f, ry = R.thr_y * 1.f, rz = R.thr_z * 1.f;
@@ -394,10 +395,10 @@ CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) 
     if (P.rr_after_escape && P.rr) (void)R.rng.next();
     R.state = S_IDLE;
   } else if (!inside) {
-    R.ncode = code_from_normal(normal);
+    R.ncode = ncode;
     R.state = S_BOUNDARY;
   } else {
-    R.ncode = code_from_normal(normal);
+    R.ncode = ncode;
     R.t = 0.f;
     R.state = S_TRACK;
   }
@@ -870,8 +871,10 @@ CVR_DEV void slot_store_dynamic(PathSlot& s, float t, uint32_t meta, const Xorwo
 }
 
 CVR_DEV int sort_key(int state) {
-  // TRACK 0, SCATTER 1, BOUNDARY 2, IDLE 3, DONE 4
-  return state == S_TRACK ? 0 : state == S_SCATTER ? 1 : (state == S_BOUNDARY || state == S_BOUNDARY_P) ? 2 : state == S_IDLE ? 3 : 4;
+  // TRACK 0, SCATTER 1, BOUNDARY / BOUNDARY_P 2, IDLE 3, everything else (DONE) 4: a packed
+  // 3-bit table indexed by the state (IDLE 0, ISECT 1, TRACK 2, SCATTER 3, BOUNDARY 4, DONE 5, BOUNDARY_P 6)
+  constexpr uint32_t kTable = 3u | (4u << 3) | (0u << 6) | (1u << 9) | (2u << 12) | (4u << 15) | (2u << 18) | (4u << 21);
+  return (int)((kTable >> (3u * (uint32_t)state)) & 7u);
 }
 
 template <int RNGM, int LAYOUT, bool COUNT>

@@ -52,7 +52,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed regions: ONE nvidia-smi process in
+    loop mode (-lms 200), started before the timed region and killed at the end of the run, as in
+    the profiling recipe.  (Spawning one nvidia-smi per sample stalled CUDA calls of this process
+    for 100-500 ms whenever one of them exited: seen as outliers among the 66 ms e2e steps.)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -60,33 +63,57 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self._stop = threading.Event()
+        self.rows = []      # (time, fields)
+        self.window = None  # (t0, t1) of the device-timed region
+        self._p = None
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
+        try:
+            for line in self._p.stdout:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 9:
+                    self.rows.append((time.perf_counter(), f))
+        except Exception:
+            pass
+
+    def start(self):
+        if os.environ.get("CVR_BENCH_NO_CLOCKS"):  # diagnosis only
+            return self
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                        "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self._p = None
+        return self
+
+    def stop(self):
+        if self._p is not None:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                self._p.terminate()
+                self._p.wait(timeout=5)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._p = None
 
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+    def __enter__(self):  # marks the device-timed region
+        if self._p is None:
+            self.start()
+        self._w0 = time.perf_counter()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        self.window = (self._w0, time.perf_counter())
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        rows = [f for t, f in self.rows if self.window is None or self.window[0] - 0.25 <= t <= self.window[1] + 0.25]
+        if not rows:
+            rows = [f for _, f in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -292,11 +319,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(n_e2e):
+        ts = time.perf_counter()
         step_e2e()
+        if os.environ.get("CVR_BENCH_DEBUG"):
+            print(f"[bench] e2e step {(time.perf_counter() - ts) * 1e3:.2f} ms", file=sys.stderr)
     e1.record(stream)
     barrier()
     wall = (time.perf_counter() - t0) * 1e3
     ms_e2e = max(e0.elapsed_time(e1), wall)  # host-side copies are part of the call: take the wall clock
+    clk.stop()
     if dist is not None:
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -9,12 +9,15 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "cvr_kernels.cuh"
@@ -82,6 +85,9 @@ struct cvr_renderer {
   uint32_t maj_dim[3] = {0, 0, 0};
   float* d_majorant2 = nullptr;  // second level: max over 8^3 bricks
   uint32_t maj2_dim[3] = {0, 0, 0};
+  std::vector<std::pair<void*, size_t>> parked;  // freed volume blocks kept for an equal-sized request
+  size_t parked_bytes = 0;
+  std::unordered_map<void*, size_t> block_bytes;  // size of every live volume block
   uint32_t* d_btable = nullptr;  // brick layout: slot table over the brick grid
   uint64_t n_bricks = 0;         // brick layout: stored bricks (without the zero brick)
   unsigned long long* d_head = nullptr;
@@ -127,6 +133,24 @@ int fail(cvr_handle h, const char* fmt, ...) {
     cudaError_t e_ = (call);                                                            \
     if (e_ != cudaSuccess) return fail(h, "%s failed: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
+
+// CVR_TRACE_SLOW=<ms>: print host-side phases of cvr_set_scene / cvr_render_image that took longer
+struct PhaseTimer {
+  const char* what;
+  double limit_ms;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(const char* w) : what(w), limit_ms(-1.0) {
+    if (const char* e = getenv("CVR_TRACE_SLOW")) limit_ms = atof(e);
+    t0 = std::chrono::steady_clock::now();
+  }
+  void mark(const char* phase) {
+    if (limit_ms < 0) return;
+    auto t1 = std::chrono::steady_clock::now();
+    double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (ms >= limit_ms) fprintf(stderr, "[cvr] %s: %s took %.2f ms\n", what, phase, ms);
+    t0 = t1;
+  }
+};
 
 #define CVR_CHECK_HANDLE(h) \
   if (!(h)) return fail(nullptr, "null handle")
@@ -221,11 +245,44 @@ int set_device(cvr_handle h) {
 }
 
 // Volume memory comes from the device's stream-ordered pool with an unlimited release
-// threshold: cudaMalloc / cudaFree of 10^8-byte blocks cost anything between 5 and 250 ms per
-// cvr_set_scene on this driver (measured), the pool hands the same blocks back in microseconds.
-cudaError_t vol_alloc(cvr_handle h, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, h->stream); }
+// threshold (cudaMalloc / cudaFree of 10^8-byte blocks cost anything between 5 and 250 ms per
+// cvr_set_scene on this driver), and blocks a scene change frees are first parked in the handle
+// and handed back to a request of exactly the same size: a re-upload of a same-shaped scene --
+// an animated volume, the bench's end-to-end step -- then makes NO allocator call at all.
+// (Even cudaMallocAsync stalls for 200-450 ms when an nvidia-smi query runs beside it: measured.)
+// Everything is ordered on the handle's stream, so a parked block can be rewritten at once.
+cudaError_t vol_alloc(cvr_handle h, void** p, size_t bytes) {
+  bytes = bytes ? bytes : 1;
+  for (size_t i = 0; i < h->parked.size(); ++i)
+    if (h->parked[i].second == bytes) {
+      *p = h->parked[i].first;
+      h->parked_bytes -= bytes;
+      h->parked.erase(h->parked.begin() + (long)i);
+      return cudaSuccess;
+    }
+  cudaError_t e = cudaMallocAsync(p, bytes, h->stream);
+  if (e == cudaSuccess) h->block_bytes[*p] = bytes;
+  return e;
+}
 void vol_free(cvr_handle h, void* p) {
-  if (p) cudaFreeAsync(p, h->stream);
+  if (!p) return;
+  auto it = h->block_bytes.find(p);
+  const size_t bytes = it == h->block_bytes.end() ? 0 : it->second;
+  if (bytes && bytes <= (512ull << 20) && h->parked_bytes + bytes <= (1ull << 30) && h->parked.size() < 16) {
+    h->parked.emplace_back(p, bytes);
+    h->parked_bytes += bytes;
+    return;
+  }
+  if (it != h->block_bytes.end()) h->block_bytes.erase(it);
+  cudaFreeAsync(p, h->stream);
+}
+void vol_flush_parked(cvr_handle h) {
+  for (auto& b : h->parked) {
+    h->block_bytes.erase(b.first);
+    cudaFreeAsync(b.first, h->stream);
+  }
+  h->parked.clear();
+  h->parked_bytes = 0;
 }
 
 void free_volume(cvr_handle h) {
@@ -249,9 +306,9 @@ void free_volume(cvr_handle h) {
   unsigned long long reserved = 0;
   if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess &&
       cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-      reserved > (1ull << 30)) {
+      reserved > (2ull << 30)) {
     cudaStreamSynchronize(h->stream);
-    cudaMemPoolTrimTo(pool, 1ull << 30);
+    cudaMemPoolTrimTo(pool, 2ull << 30);
   }
 }
 
@@ -500,6 +557,8 @@ int cvr_release(cvr_handle h) {
   cudaStreamSynchronize(h->stream);
   collect_timing(h);
   free_volume(h);
+  vol_flush_parked(h);
+  cudaStreamSynchronize(h->stream);
   cudaFree(h->d_head);
   cudaFree(h->d_ctr);
   cudaFree(h->d_tile);
@@ -677,8 +736,11 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
   if (!(s->scale > 0.f) || !(s->max_density > 0.f))
     return fail(h, "cvr_set_scene: scale and max_density must be positive");
   if (set_device(h)) return 1;
+  PhaseTimer pt("cvr_set_scene");
   CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  pt.mark("sync");
   free_volume(h);
+  pt.mark("free_volume");
   h->scene_layout = h->layout;
   MediumParams& m = h->P.med;
   m.btable = nullptr, m.bmx = m.bmy = m.bmz = 0;
@@ -714,6 +776,7 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     CVR_CUDA(h, cudaGetLastError());
     if (build_majorant2(h)) return 1;
   }
+  pt.mark("density alloc + copy + build");
   m.albedo_const = s->albedo ? 0 : 1;
   m.albedo_r = s->albedo_const[0], m.albedo_g = s->albedo_const[1], m.albedo_b = s->albedo_const[2];
   m.anx = m.any = m.anz = 2;
@@ -730,14 +793,17 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
       CVR_CUDA(h, cudaGetLastError());
     }
   }
+  pt.mark("albedo alloc + copy + build");
   if (h->layout == LAYOUT_CELL8) {
     // the dense copies are only the source of the cell layouts
     CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+    pt.mark("sync 2");
     vol_free(h, h->d_density);
     vol_free(h, h->d_albedo);
     h->d_density = nullptr;
     h->d_albedo = nullptr;
   }
+  pt.mark("free staging");
   m.density = h->d_density;
   m.dcells = h->d_dcells;
   m.albedo = h->d_albedo;
@@ -1127,6 +1193,7 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
   if (r->n_tiles_x > r->res_x || r->n_tiles_y > r->res_y) return fail(h, "cvr_render_image: more tiles than pixels");
   if (!h->scene_set) return fail(h, "cvr_render_image before cvr_set_scene");
   if (set_device(h)) return 1;
+  PhaseTimer pt("cvr_render_image");
   const uint32_t n_tiles = r->n_tiles_x * r->n_tiles_y;
   std::vector<uint32_t> origins(2 * (size_t)n_tiles);
   uint32_t tile_dim[2];
@@ -1213,6 +1280,7 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
       CVR_CUDA(h, cudaGetLastError());
     }
   }
+  pt.mark("setup + launches (host side)");
   if (host_image) {
     for (uint32_t k = first; k < n_tiles; k += stride) {
       uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
@@ -1222,7 +1290,9 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
                                     tile_dim[1], cudaMemcpyDeviceToHost, h->stream));
     }
   }
+  pt.mark("D2H enqueue");
   CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  pt.mark("final sync (kernel + copies)");
   // what the sequence of reset() calls leaves behind after all tiles
   h->seed += n_tiles * seed_step;
   return 0;

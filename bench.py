@@ -20,8 +20,12 @@ roofline   dominant kernel k_volpt: algorithmic bytes per launch (32 B/density l
            128 B/albedo lookup + 16 B/path; the counts come from the
            kernel's own counters) / its mean launch duration (CUDA events recorded by the
            library around every launch) against MEASURED_PEAKS.json's hbm_gbs.
-cpu_baseline  the CPU oracle (plain-C port of the reference estimator; the reference
-           has no CPU renderer) on all host cores over a bounded sample of the workload.
+cpu_baseline  the reference's OWN regenerationSK kernel (d_render_single_thread_regeneration
+           and everything it calls) compiled for the host by g++ from the reference's headers
+           (oracle/_ref/libcvr_ref_cpu.so, kind "reference": one persistent CUDA thread per host
+           core sharing the reference's atomic path counter) on all host cores over a bounded
+           sample of the workload; the plain-C oracle (kind "port") only where that library is
+           absent.  The reference has no CPU renderer of its own.
 """
 from __future__ import annotations
 
@@ -136,33 +140,46 @@ def oracle_scene_and_cam(sc, res):
 
 
 def cpu_sample(sc, spp: int, seed: int = 0):
-    """CPU oracle over `spp` samples of the full 1024^2 image on all host cores."""
+    """`spp` samples of the full 1024^2 image on all host cores: the reference's own
+    regenerationSK kernel built for the host when oracle/_ref/libcvr_ref_cpu.so is present
+    (kind "reference"), else the plain-C oracle (kind "port").
+    Returns (Msamples/s, cores, seconds, paths, kind, what)."""
     B, osc, cam = oracle_scene_and_cam(sc, RES)
     cores = os.cpu_count() or 1
+    if B.ref_cpu() is not None:
+        rc = B.RefCpu(osc, cam)
+        t0 = time.perf_counter()
+        rc.render_regen(spp, seed=seed, n_threads=cores)
+        dt = time.perf_counter() - t0
+        paths = RES * RES * spp
+        return paths / dt / 1e6, cores, dt, paths, "reference", \
+            "the reference's d_render_single_thread_regeneration compiled for the host (oracle/_ref/libcvr_ref_cpu.so)"
     t0 = time.perf_counter()
     _, ctr = B.render_regen(osc, cam, spp, seed=seed, rng_mode=1, n_threads=cores)
     dt = time.perf_counter() - t0
-    return ctr["paths"] / dt / 1e6, cores, dt, ctr
+    return ctr["paths"] / dt / 1e6, cores, dt, ctr["paths"], "port", "oracle/cvr_oracle.c regenerationSK path loop"
 
 
 def run_reference(args, rank: int):
     """Reference arm: the reference has no CPU renderer and cannot be pip-installed (it
-    is a CMake/vcpkg C++ executable), so this arm times the CPU oracle -- the
-    plain-C port of its estimator -- on all host cores; each step is a bounded sample
-    (1024x1024 at 1 spp) of the same workload."""
+    is a CMake/vcpkg C++ executable), so this arm times the reference's own
+    regenerationSK kernel compiled for the host from its headers (oracle/_ref/libcvr_ref_cpu.so;
+    the plain-C oracle where that is absent) on all host cores; each step is a bounded sample
+    (1024x1024 at 2 spp) of the same workload."""
     if rank != 0:
         return
     from cudavolumerenderer_b200 import scenes
 
     sc = scenes.hetvol()
-    spp = 1
+    spp = 2
     for _ in range(args.warmup):
         cpu_sample(sc, spp)
     t0 = time.perf_counter()
     paths = 0
+    kind = what = None
     for s in range(args.steps):
-        _, cores, _, ctr = cpu_sample(sc, spp, seed=s * RES * RES)
-        paths += ctr["paths"]
+        _, cores, _, n, kind, what = cpu_sample(sc, spp, seed=s * RES * RES * spp)
+        paths += n
     dt = time.perf_counter() - t0
     v = paths / dt / 1e6
     line = {
@@ -171,8 +188,8 @@ def run_reference(args, rank: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{RES}x{RES} at {spp} spp per step"},
-        "cpu_baseline": {"value": v, "unit": METRIC, "cores": cores, "kind": "port",
-                         "sample": f"{RES}x{RES} at {spp} spp per step, oracle/cvr_oracle.c regenerationSK path loop"},
+        "cpu_baseline": {"value": v, "unit": METRIC, "cores": cores, "kind": kind,
+                         "sample": f"{RES}x{RES} at {spp} spp per step, {what}"},
         "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -375,9 +392,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     cpu = None
     ref_gpu = None
     if world == 1:
-        v, cores, dt, _ = cpu_sample(sc, 8)
-        cpu = {"value": v, "unit": METRIC, "cores": cores, "kind": "port",
-               "sample": f"{RES}x{RES} at 8 spp ({dt:.1f} s), oracle/cvr_oracle.c regenerationSK path loop"}
+        cpu_spp = 16
+        v, cores, dt, _, kind, what = cpu_sample(sc, cpu_spp)
+        cpu = {"value": v, "unit": METRIC, "cores": cores, "kind": kind,
+               "sample": f"{RES}x{RES} at {cpu_spp} spp ({dt:.1f} s), {what}"}
         ref_gpu = ref_gpu_baseline(sc, SPP, rgb.float().cpu().numpy())
 
     line = {

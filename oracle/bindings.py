@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libcvr_oracle.so")
 REF_HOST_SO = os.path.join(HERE, "_ref", "libcvr_ref_host.so")
 REF_GPU_SO = os.path.join(HERE, "_ref", "libcvr_ref_gpu.so")
+REF_CPU_SO = os.path.join(HERE, "_ref", "libcvr_ref_cpu.so")
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -101,6 +102,8 @@ def lib() -> C.CDLL:
         L.cvro_ggx_g1.restype = C.c_float
         L.cvro_density_lookup.argtypes = [C.POINTER(Scene), f32p]
         L.cvro_density_lookup.restype = C.c_float
+        L.cvro_woodcock.argtypes = [C.POINTER(Scene), f32p, f32p, C.c_float, C.c_int32, C.POINTER(C.c_int)]
+        L.cvro_woodcock.restype = C.c_float
         L.cvro_albedo_lookup.argtypes = [C.POINTER(Scene), f32p, f32p]
         L.cvro_camera_ray.argtypes = [C.POINTER(Camera), C.c_uint32, C.c_float, C.c_float, f32p, f32p]
         L.cvro_utilhash.argtypes = [C.c_uint32]
@@ -144,6 +147,84 @@ def ref_host():
         R.ref_fmaxf3.restype = C.c_float
         _ref_host = R
     return _ref_host
+
+
+_ref_cpu = None
+
+
+def ref_cpu():
+    """The reference's own naiveSK / regenerationSK kernels compiled for the host by g++
+    (oracle/ref_cpu_harness.cpp), or None when not built."""
+    global _ref_cpu
+    if _ref_cpu is None:
+        if not os.path.exists(REF_CPU_SO):
+            return None
+        R = C.CDLL(REF_CPU_SO)
+        R.refcpu_set_scene.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int,
+                                       f32p, f32p, C.c_float, C.c_float]
+        R.refcpu_set_scene.restype = None
+        R.refcpu_set_camera.argtypes = [f32p, f32p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_uint, C.c_uint]
+        R.refcpu_set_camera.restype = None
+        R.refcpu_ggx_defaults.argtypes = [f32p, f32p]
+        R.refcpu_render_naive.argtypes = [C.c_uint64, C.c_uint64, f32p, C.c_int]
+        R.refcpu_render_naive.restype = None
+        R.refcpu_trace_paths_naive.argtypes = [C.c_uint64, C.c_uint64, f32p, C.c_int]
+        R.refcpu_trace_paths_naive.restype = None
+        R.refcpu_render_regen.argtypes = [C.c_uint64, C.c_uint, f32p, C.c_int]
+        R.refcpu_render_regen.restype = None
+        R.refcpu_density.argtypes = [f32p]
+        R.refcpu_density.restype = C.c_float
+        R.refcpu_albedo_at_world.argtypes = [f32p, f32p]
+        R.refcpu_camera_ray.argtypes = [C.c_uint, C.c_int, f32p, f32p]
+        R.refcpu_woodcock.argtypes = [f32p, f32p, C.c_float, C.c_int, C.POINTER(C.c_int)]
+        R.refcpu_woodcock.restype = C.c_float
+        R.refcpu_trace_one_naive.argtypes = [C.c_uint, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        R.refcpu_trace_one_naive.restype = None
+        R.refcpu_ggx_g1.argtypes = [f32p] * 3
+        R.refcpu_ggx_g1.restype = C.c_float
+        R.refcpu_ggx_sample.argtypes = [f32p, C.c_int, f32p, f32p]
+        R.refcpu_ggx_sample.restype = C.c_int
+        _ref_cpu = R
+    return _ref_cpu
+
+
+class RefCpu:
+    """One scene + camera loaded into the host-compiled reference kernels (process-global
+    state, like the reference's __constant__ symbols: one instance at a time)."""
+
+    def __init__(self, scene: "Scene", cam: "Camera"):
+        R = ref_cpu()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libcvr_ref_cpu.so is not built (needs /root/reference)")
+        self.R = R
+        self._keep = scene._keep  # the arrays are borrowed by the library
+        R.refcpu_set_scene(scene.density, scene.dnx, scene.dny, scene.dnz, scene.albedo, scene.anx, scene.any,
+                           scene.anz, scene.box_min, scene.box_max, scene.scale, scene.max_density)
+        self.w, self.h = int(cam.resolution[0]), int(cam.resolution[1])
+        R.refcpu_set_camera(cam.inv_view, cam.raster_to_view, self.w, self.h, cam.pixel_index_range[0],
+                            cam.pixel_index_range[1], cam.offset[0], cam.offset[1])
+
+    def trace_paths_naive(self, first: int, count: int, n_threads: int | None = None) -> np.ndarray:
+        out = np.zeros((count, 4), np.float32)
+        self.R.refcpu_trace_paths_naive(first, count, fp(out), n_threads or os.cpu_count() or 1)
+        return out
+
+    def trace_one_naive(self, tid: int):
+        """(rgba, uniforms drawn, texels fetched) of one naiveSK path."""
+        out = np.zeros(4, np.float32)
+        nd, nt = C.c_uint64(), C.c_uint64()
+        self.R.refcpu_trace_one_naive(tid, fp(out), C.byref(nd), C.byref(nt))
+        return out, int(nd.value), int(nt.value)
+
+    def render_naive(self, iterations: int, n_threads: int | None = None) -> np.ndarray:
+        out = np.zeros((self.h, self.w, 4), np.float32)
+        self.R.refcpu_render_naive(0, self.w * self.h * iterations, fp(out), n_threads or os.cpu_count() or 1)
+        return out
+
+    def render_regen(self, iterations: int, seed: int = 0, n_threads: int | None = None) -> np.ndarray:
+        out = np.zeros((self.h, self.w, 4), np.float32)
+        self.R.refcpu_render_regen(self.w * self.h * iterations, seed, fp(out), n_threads or os.cpu_count() or 1)
+        return out
 
 
 def fp(a: np.ndarray):

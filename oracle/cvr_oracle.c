@@ -479,6 +479,19 @@ static float woodcock(const cvro_scene* sc, v3 o, v3 d, float max_t, cvro_rng* r
   return t;
 }
 
+/* unit pin of the above against the reference's own woodcockTracking (host-compiled,
+ * oracle/ref_cpu_harness.cpp): Rng(seed), one call, returns t */
+float cvro_woodcock(const cvro_scene* sc, const float o[3], const float d[3], float max_t,
+                    int32_t seed, int* scattered) {
+  cvro_rng r;
+  cvro_counters c;
+  memset(&c, 0, sizeof c);
+  cvro_rng_init(&r, seed);
+  float t = woodcock(sc, V(o[0], o[1], o[2]), V(d[0], d[1], d[2]), max_t, &r, &c);
+  *scattered = t < max_t;
+  return t;
+}
+
 /* ------------------------------------------------------------------------- */
 /* the path loop (NaiveVolPTsk_kernel.cuh:22-86 /                                */
 /* RegenerationVolPTsk_kernel.cuh:169-229)                                       */

@@ -9,17 +9,23 @@
  *
  * Parity pin: the reference ships no tests, golden vectors or CPU renderer
  * (SURVEY.md section 8(c)), so this oracle is pinned against the reference ITSELF
- * run here:  oracle/_ref/libcvr_ref_host.so host-compiles the reference's own
- * __host__ __device__ functions (AABB::intersect, Frame, ImportanceSampleHG,
- * GGX_sample, fresnelDielectric, GGX_G1, morton3D, utilhash) from the headers
- * where they lie under /root/reference and tests/test_oracle_vs_ref_host.py checks
- * this file against them bit for bit; tests/golden/ holds vectors generated from
- * that library (script committed) so the pin also travels to boxes without the
- * reference.  The XORWOW stream is pinned against cuRAND's device generator on
- * the GPU (tests/test_gpu_rng.py) and against committed golden words.
- * The device-only glue (Woodcock loop, trilinear lookup, path loop) cannot be
- * host-compiled from the reference; it is restated here and checked against the
- * reference's own kernels compiled for sm_100a (oracle/_ref/libcvr_ref_gpu.so).
+ * run here, three ways (recipes in oracle/Makefile, outputs in oracle/_ref/):
+ *  1. WHOLE PATHS, bit for bit: oracle/_ref/libcvr_ref_cpu.so is the reference's own
+ *     NaiveVolPTsk_kernel::d_render and RegenerationVolPTsk_kernel::
+ *     d_render_single_thread_regeneration -- with woodcockTracking, DeviceVolume::
+ *     operator(), indexToCameraRay, AABB::intersect, GGX::sample, HG::sample,
+ *     atomicVectorAdd -- compiled for the host by g++ from the headers where they lie
+ *     (oracle/ref_cpu_harness.cpp supplies only what the CUDA platform provides:
+ *     thread indices, atomicAdd, a host XORWOW behind the Rng interface, the point-sampled
+ *     clamped texture fetch).  tests/test_oracle.py requires every per-path radiance and
+ *     every single-stream regenerationSK image of this file to EQUAL that build's, live
+ *     and against tests/golden/ref_cpu_paths.npz (generated from it, script committed).
+ *  2. Per function: oracle/_ref/libcvr_ref_host.so host-compiles the reference's
+ *     __host__ __device__ functions through nvcc (AABB::intersect, Frame,
+ *     ImportanceSampleHG, GGX_sample, fresnelDielectric, GGX_G1, morton3D, utilhash);
+ *     checked bit for bit live and against tests/golden/ref_host_golden.npz.
+ *  3. On the GPU: the reference's own kernels compiled for sm_100a
+ *     (oracle/_ref/libcvr_ref_gpu.so) and cuRAND's device XORWOW (tests/test_gpu_parity.py).
  */
 #ifndef CVR_ORACLE_H_
 #define CVR_ORACLE_H_
@@ -125,6 +131,8 @@ float cvro_fresnel_dielectric(float eta, float ndotwi, float* ndotwt);
 float cvro_ggx_g1(const float alpha[2], const float v[3], const float m[3]);
 float cvro_density_lookup(const cvro_scene* sc, const float p01[3]);
 void cvro_albedo_lookup(const cvro_scene* sc, const float p01[3], float rgb[3]);
+float cvro_woodcock(const cvro_scene* sc, const float o[3], const float d[3], float max_t,
+                    int32_t seed, int* scattered);
 void cvro_camera_ray(const cvro_camera* cam, uint32_t image_id, float u0, float u1,
                      float o[3], float d[3]);
 uint32_t cvro_utilhash(uint32_t a);

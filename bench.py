@@ -374,7 +374,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     grid, block, regs = kl.launchShape()
     # measured random-32-B-sector gather peak at this volume's device footprint (L2-resident here)
     nz, ny, nx = sc.density.shape
-    footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 128)  # density + albedo cell8 layouts
+    footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 96)  # density cells + rgb albedo cells
     gather_peak = kl.gatherRoofline(footprint, 512, 8)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,

@@ -39,6 +39,7 @@ class Counters(C.Structure):
         ("paths", C.c_uint64), ("bounces", C.c_uint64), ("density_lookups", C.c_uint64),
         ("albedo_lookups", C.c_uint64), ("escaped", C.c_uint64),
         ("speculative_lookups", C.c_uint64), ("launches", C.c_uint64), ("kernel_ms", C.c_double),
+        ("skipped_fetches", C.c_uint64),
     ]
 
     def as_dict(self):

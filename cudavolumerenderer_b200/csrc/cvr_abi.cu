@@ -66,6 +66,7 @@ struct cvr_renderer {
   int track_min_lanes = 12;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
   int fix_nan = 0;
+  int skip = -1;  // fetch-skip table (cvr_kernels.cuh: SkipTab): -1 = auto (on where it applies), 0, 1
 
   // launcher state
   KernelParams P{};
@@ -80,7 +81,7 @@ struct cvr_renderer {
   float* d_density = nullptr;
   float* d_dcells = nullptr;
   float4* d_albedo = nullptr;
-  float4* d_acells = nullptr;
+  float* d_acells = nullptr;  // AlbedoCell layout, CVR_ACELL_FLOATS floats per cell
   float* d_majorant = nullptr;
   uint32_t maj_dim[3] = {0, 0, 0};
   float* d_majorant2 = nullptr;  // second level: max over 8^3 bricks
@@ -88,6 +89,10 @@ struct cvr_renderer {
   std::vector<std::pair<void*, size_t>> parked;  // freed volume blocks kept for an equal-sized request
   size_t parked_bytes = 0;
   std::unordered_map<void*, size_t> block_bytes;  // size of every live volume block
+  uint8_t* d_skip = nullptr;     // fetch-skip table (global copy; the kernel stages it in shared memory)
+  size_t skip_bytes = 0;         // padded to 4 bytes; 0 = the selected kernel runs without it
+  uint32_t skip_shift = 0, skip_dim[3] = {0, 0, 0};
+  bool skip_dirty = true;        // scene or table geometry changed since the table was built
   uint32_t* d_btable = nullptr;  // brick layout: slot table over the brick grid
   uint64_t n_bricks = 0;         // brick layout: stored bricks (without the zero brick)
   unsigned long long* d_head = nullptr;
@@ -158,7 +163,20 @@ struct PhaseTimer {
 typedef void (*kernel_fn)(const KernelParams);
 
 template <int W>
-kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int tracking) {
+kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int tracking, int skip) {
+  if (skip) {  // fetch-skip table: fused arithmetic, global majorant, cell layouts (one 896-thread CTA per SM)
+    if (exact || tracking || layout == LAYOUT_LINEAR) return nullptr;
+#define CVR_KS(R, L)                                                                      \
+  if (rng_mode == R && layout == L)                                                       \
+    return count ? (kernel_fn)k_volpt_warp<R, L, true, true, false, W, true>              \
+                 : (kernel_fn)k_volpt_warp<R, L, false, true, false, W, true>;
+    CVR_KS(RNG_XORWOW_PATH, LAYOUT_CELL8)
+    CVR_KS(RNG_XORWOW_PATH, LAYOUT_BRICK)
+    CVR_KS(RNG_XORWOW_THREAD, LAYOUT_CELL8)
+    CVR_KS(RNG_XORWOW_THREAD, LAYOUT_BRICK)
+#undef CVR_KS
+    return nullptr;
+  }
   if (layout == LAYOUT_BRICK) {  // sparse bricks: fused arithmetic only, global or local majorant
 #define CVR_KB(R, LOCAL)                                                                              \
   if (rng_mode == R && tracking == LOCAL)                                                             \
@@ -194,10 +212,11 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
   return nullptr;
 }
 
-kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1, int tracking = 0, int wslots = 64) {
+kernel_fn pick_kernel(int sched, int rng_mode, int layout, int count, int exact = 1, int tracking = 0, int wslots = 64,
+                      int skip = 0) {
   if (sched == 3)
-    return wslots == 96 ? pick_warp_kernel<96>(rng_mode, layout, count, exact, tracking)
-                        : pick_warp_kernel<64>(rng_mode, layout, count, exact, tracking);
+    return wslots == 96 ? pick_warp_kernel<96>(rng_mode, layout, count, exact, tracking, skip)
+                        : pick_warp_kernel<64>(rng_mode, layout, count, exact, tracking, skip);
   if (tracking == 1) {
     if (sched != 2 || layout != LAYOUT_CELL8) return nullptr;
     if (rng_mode == RNG_XORWOW_PATH)
@@ -294,11 +313,15 @@ void free_volume(cvr_handle h) {
   vol_free(h, h->d_majorant2);
   h->d_majorant2 = nullptr;
   vol_free(h, h->d_btable);
+  vol_free(h, h->d_skip);
+  h->d_skip = nullptr;
+  h->skip_dirty = true;
   h->d_majorant = nullptr;
   h->d_btable = nullptr;
   h->n_bricks = 0;
   h->d_density = h->d_dcells = nullptr;
-  h->d_albedo = h->d_acells = nullptr;
+  h->d_albedo = nullptr;
+  h->d_acells = nullptr;
   h->scene_set = false;
   // a multi-GB volume must not stay parked in the pool (other allocators of the process --
   // torch, the caller's cudaMalloc -- cannot see it): give everything above 1 GiB back
@@ -336,14 +359,75 @@ int effective_wslots(cvr_handle h) {
 // 1026 / 1050, sparse 2048^3 1612 / 2058 -- on by default, also for HBM-resident volumes.
 int effective_pair(cvr_handle h) { return h->pair >= 0 ? h->pair : 1; }
 
+// The fetch-skip table applies to the fused global-majorant loop of the warp scheduler over a
+// cell layout; "auto" turns it on there.
+bool skip_wanted(cvr_handle h) {
+  if (h->sched != 3 || h->exact || h->tracking || h->scene_layout == LAYOUT_LINEAR || h->rng_mode == RNG_PHILOX)
+    return false;
+  if (!h->d_majorant || !h->maj_dim[0]) return false;
+  // auto: on for volumes beyond the L2.  Measured on B200 (1024^2 x 16 spp, Msamples/s off / on):
+  // manix 2526 / 2744, fbm 512^3 1079 / 1480, sparse 1024^3 2447 / 2475 -- but bucky 5679 / 5196 and
+  // hetvol 985 / 945: an L2-resident volume has no bandwidth to save and pays the ~30 extra
+  // instructions per pair of steps.
+  if (h->skip < 0) return h->volume_bytes > (size_t)h->l2_bytes;
+  return h->skip != 0;
+}
+
 int effective_block(cvr_handle h) {
+  if (h->sched == 3 && h->skip_bytes) return CVR_WSKIP_BLOCK;  // the table offset is compiled for this CTA size
   const int cap = h->sched == 3 ? CVR_WBLOCK : CVR_BLOCK;
   return (h->block > 0 && h->block <= cap) ? h->block : cap;
 }
 
+// Table geometry: the finest brick edge (8 << e cells) whose byte-per-brick table fits the shared
+// memory left beside the slots of ONE CTA of CVR_WSKIP_BLOCK threads; skip_bytes = 0 when no
+// level up to 64^3-cell bricks fits (the kernel then runs without the table).
+void plan_skip_table(cvr_handle h, size_t smem_optin) {
+  h->skip_bytes = 0;
+  if (!skip_wanted(h)) return;
+  const size_t slots = warp_sched_smem_bytes(CVR_WSKIP_BLOCK, effective_wslots(h));
+  if (slots + 64 > smem_optin) return;
+  const size_t budget = smem_optin - slots;
+  for (uint32_t e = 0; e <= 3; ++e) {
+    uint32_t d[3];
+    for (int a = 0; a < 3; ++a) d[a] = (h->maj_dim[a] + (1u << e) - 1) >> e;
+    const size_t n = ((size_t)d[0] * d[1] * d[2] + 3) & ~(size_t)3;
+    if (n <= budget) {
+      if (h->skip_shift != CVR_BRICK_LOG2 + e || h->skip_dim[0] != d[0] || h->skip_dim[1] != d[1] || h->skip_dim[2] != d[2])
+        h->skip_dirty = true;
+      h->skip_shift = CVR_BRICK_LOG2 + e;
+      h->skip_dim[0] = d[0], h->skip_dim[1] = d[1], h->skip_dim[2] = d[2];
+      h->skip_bytes = n;
+      return;
+    }
+  }
+}
+
+// (re)build the table for the scene in place; needs P.inv.sig_ratio (fill_track_inv)
+int build_skip_table(cvr_handle h) {
+  if (!h->skip_bytes || !h->skip_dirty) return 0;
+  vol_free(h, h->d_skip);
+  h->d_skip = nullptr;
+  CVR_CUDA(h, vol_alloc(h, (void**)&h->d_skip, h->skip_bytes));
+  CVR_CUDA(h, cudaMemsetAsync(h->d_skip, 0xff, h->skip_bytes, h->stream));  // padding bytes: never skip
+  const uint32_t n = h->skip_dim[0] * h->skip_dim[1] * h->skip_dim[2];
+  k_build_skip_table<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_majorant, h->maj_dim[0], h->maj_dim[1], h->maj_dim[2],
+                                                             h->skip_shift - CVR_BRICK_LOG2, h->skip_dim[0], h->skip_dim[1],
+                                                             h->skip_dim[2], h->P.inv.sig_ratio, h->d_skip);
+  CVR_CUDA(h, cudaGetLastError());
+  h->skip_dirty = false;
+  return 0;
+}
+
 int ensure_init(cvr_handle h) {
   if (h->inited) return 0;
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h));
+  {
+    int optin = 0;
+    CVR_CUDA(h, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    plan_skip_table(h, (size_t)optin);
+  }
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h),
+                            h->skip_bytes != 0);
   if (!k)
     return fail(h, "no kernel for sched=%d rng=%d layout=%d exact=%d (philox needs sched=lane; sparse scenes need sched=warp, exact=0)",
                 h->sched, h->rng_mode, h->scene_layout, h->exact);
@@ -351,7 +435,7 @@ int ensure_init(cvr_handle h) {
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
   // the warp-private scheduler keeps its path slots in DYNAMIC shared memory (may exceed 48 KB)
-  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(effective_block(h), effective_wslots(h)) : 0;
+  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(effective_block(h), effective_wslots(h), h->skip_bytes) : 0;
   if (h->smem_bytes)
     CVR_CUDA(h, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int per_sm = 0;
@@ -450,7 +534,14 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.pullback = (h->variant != VAR_REGEN) ? 1 : 0;
   P.rr_after_escape = (h->variant != VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD) ? 1 : 0;
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
-  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h));
+  if (build_skip_table(h)) return 1;
+  P.skip_tab = h->d_skip;
+  P.skip_n = (uint32_t)h->skip_bytes;
+  P.skip_shift = h->skip_shift;
+  P.skip_bx = h->skip_dim[0];
+  P.skip_bxy = h->skip_dim[0] * h->skip_dim[1];
+  kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h),
+                            h->skip_bytes != 0);
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
@@ -648,6 +739,9 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     h->policy = atoi(value);
   } else if (k == "pair") {
     h->pair = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
+  } else if (k == "skip") {
+    h->skip = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
+    h->inited = false;
   } else if (k == "warp_slots") {
     if (v == "auto")
       h->warp_slots = 0;
@@ -703,6 +797,8 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(h->policy);
   else if (k == "pair")
     v = std::to_string(effective_pair(h));
+  else if (k == "skip")  // "0" or the brick edge in cells the table was planned with (after the first launch / init)
+    v = h->skip_bytes ? std::to_string(1u << h->skip_shift) : std::string(skip_wanted(h) && !h->inited ? "auto" : "0");
   else if (k == "warp_slots")
     v = std::to_string(effective_wslots(h));
   else if (k == "track_steps")
@@ -787,7 +883,7 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     CVR_CUDA(h, cudaMemcpyAsync(h->d_albedo, s->albedo, na * sizeof(float4), kind, h->stream));
     if (h->layout == LAYOUT_CELL8) {
       size_t ncell = (size_t)(m.anx + 1) * (m.any + 1) * (m.anz + 1);
-      CVR_CUDA(h, vol_alloc(h, (void**)&h->d_acells, ncell * 8 * sizeof(float4)));
+      CVR_CUDA(h, vol_alloc(h, (void**)&h->d_acells, ncell * CVR_ACELL_FLOATS * sizeof(float)));
       int g = (int)std::min<size_t>((ncell * 8 + bt - 1) / bt, (size_t)h->sm_count * 32);
       k_build_albedo_cells<<<g, bt, 0, h->stream>>>(h->d_albedo, m.anx, m.any, m.anz, h->d_acells);
       CVR_CUDA(h, cudaGetLastError());
@@ -814,6 +910,8 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     if (effective_wslots(h) != before) h->inited = false;  // another kernel instantiation
   }
   h->scene_set = true;
+  h->skip_dirty = true;  // new majorants: the fetch-skip table is planned and built again at the next launch
+  h->inited = false;
   return 0;
 }
 
@@ -929,6 +1027,8 @@ int cvr_set_scene_sparse(cvr_handle h, const cvr_sparse_desc* s) {
   h->P.med.max_density = s->max_density > 0.f ? s->max_density : mx;  // VDBSceneBuilder.h:54-55: max voxel
   if (!(h->P.med.max_density > 0.f)) return fail(h, "cvr_set_scene_sparse: the volume is empty");
   h->scene_set = true;
+  h->skip_dirty = true;  // new majorants: the fetch-skip table is planned and built again at the next launch
+  h->inited = false;
   return 0;
 }
 
@@ -979,6 +1079,8 @@ int cvr_set_scene_procedural(cvr_handle h, const char* kind_c, int32_t n, uint32
   h->P.med.max_density = s->max_density > 0.f ? s->max_density : (mx > 0.f ? mx : 1.f);
   if (max_density_out) *max_density_out = h->P.med.max_density;
   h->scene_set = true;
+  h->skip_dirty = true;  // new majorants: the fetch-skip table is planned and built again at the next launch
+  h->inited = false;
   return 0;
 }
 
@@ -1115,6 +1217,7 @@ int cvr_get_counters(cvr_handle h, cvr_counters* out) {
     out->paths = c.paths, out->bounces = c.bounces, out->density_lookups = c.density_lookups;
     out->albedo_lookups = c.albedo_lookups, out->escaped = c.escaped;
     out->speculative_lookups = c.speculative;
+    out->skipped_fetches = c.skipped;
   }
   out->launches = h->launches;
   out->kernel_ms = h->kernel_ms;

@@ -31,7 +31,7 @@ enum : int { RNG_XORWOW_PATH = 0, RNG_XORWOW_THREAD = 1, RNG_PHILOX = 2 };
 enum : int { LAYOUT_LINEAR = 0, LAYOUT_CELL8 = 1, LAYOUT_BRICK = 2 };
 
 struct DeviceCounters {
-  unsigned long long paths, bounces, density_lookups, albedo_lookups, escaped, speculative;
+  unsigned long long paths, bounces, density_lookups, albedo_lookups, escaped, speculative, skipped;
 };
 
 struct TrackInv {
@@ -90,6 +90,10 @@ struct KernelParams {
   int fix_nan;          // drop non-finite path contributions (reference quirk opt-out, default 0)
   int pair;             // fast tracking loop: two Woodcock steps per iteration, the second speculative
   int policy;           // warp scheduler: 0 = fullest state wins, 1 = events first unless a full tracking batch waits
+  // fetch-skip table (warp scheduler, fused arithmetic, global majorant; see SkipTab below)
+  const uint8_t* skip_tab;  // one byte per brick of (1 << skip_shift)^3 lookup cells, x fastest
+  uint32_t skip_n;          // bytes in the table (0 = feature off)
+  uint32_t skip_shift, skip_bx, skip_bxy;  // brick edge = 1 << shift cells; row / slice strides in bricks
 };
 
 // S_BOUNDARY_P = boundary event whose FIRST uniform is already drawn and parked in
@@ -150,7 +154,7 @@ struct PathRegs {
 };
 
 struct LaneCounters {
-  uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0, spec = 0;
+  uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0, spec = 0, skip = 0;
 };
 
 // Loop invariants of the Woodcock step (the reference recomputes them every
@@ -246,6 +250,54 @@ CVR_DEV void cell_fetch(const MediumParams& m, const TrackInv& I, float cx, floa
   ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
   F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
 }
+// ---- fetch-skip table ----------------------------------------------------------------------
+// The Woodcock loop is bound by the L1TEX wavefront rate, not by bytes or issue slots: every
+// lane of a warp looks up a different 32-byte cell, so one LDG.256 is ~21 wavefronts, and the
+// random-sector gather microbenchmark tops out at ~0.4 sectors / cycle / SM -- the rate this
+// kernel already runs at.  The only way past it is to fetch less.  A step whose
+// accept draw w exceeds (brick majorant) * sig_ratio is a null collision WHATEVER the cell
+// holds: density <= majorant, the multiply is monotonic, so `density * sig_ratio < w` is
+// certain.  The cell load of such a step is skipped.  RNG consumption, the accept decision and
+// therefore every path are unchanged bit for bit (unlike tracking=local, which changes the
+// sequence); only the number of gathers drops (hetvol -53 %, manix -90 %).
+// The majorant lives in SHARED memory (a global table would cost the same wavefront as the
+// cell): one byte per brick of (1 << shift)^3 cells, s = ceil(r * 256 * (1 + 1e-5)) - 1 clamped
+// to [0, 255] with r = majorant * sig_ratio in [0, 1]; the test is on the TOP BYTE of the raw
+// XORWOW word behind w (w > top / 256): top > s  =>  w > (s + 1) / 256 >= r.  The 1e-5 margin
+// covers the few ulps a fused trilinear blend can exceed the largest corner by; s = 255 never
+// skips.  Skipped lanes load cell 0 instead (one line shared by all of them).
+// The geometry (shift, strides) stays in the kernel-parameter constant bank and the table sits at
+// a compile-time offset of the dynamic shared memory, so the test costs no registers.
+struct SkipTab {
+  const uint8_t* tab;  // shared memory
+};
+template <bool SKIP>
+CVR_DEV bool skip_test(const KernelParams& P, const SkipTab& S, uint32_t kx, uint32_t ky, uint32_t kz, uint32_t w_word) {
+  if (!SKIP) return false;
+  const uint32_t b = (kx >> P.skip_shift) + (ky >> P.skip_shift) * P.skip_bx + (kz >> P.skip_shift) * P.skip_bxy;
+  return (w_word >> 24) > (uint32_t)S.tab[b];
+}
+// cell_fetch with the skip test between the address and the load
+template <int LAYOUT, bool SKIP>
+CVR_DEV bool cell_fetch_skip(const KernelParams& P, const TrackInv& I, const SkipTab& S, float cx, float cy, float cz,
+                             uint32_t w_word, CellFetch& F) {
+  const MediumParams& m = P.med;
+  const float bx = __fadd_rd(cx, CVR_FLOOR_MAGIC), by = __fadd_rd(cy, CVR_FLOOR_MAGIC), bz = __fadd_rd(cz, CVR_FLOOR_MAGIC);
+  uint32_t kx = min((uint32_t)(__float_as_int(bx) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nx),
+           ky = min((uint32_t)(__float_as_int(by) - (CVR_FLOOR_MAGIC_BITS - 1)), I.ny),
+           kz = min((uint32_t)(__float_as_int(bz) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nz);
+  const bool skip = skip_test<SKIP>(P, S, kx, ky, kz, w_word);
+  // a skipped lane loads cell 0 instead: any resident cell will do, the caller ignores the blend.
+  // (Predicating the lane off the load was measured and rejected: it does save the lane's L1
+  // data-pipe wavefront -- the pipe charges one per ACTIVE lane of an LDG.256 wherever it points --
+  // but the destination registers then need a definition (4 CS2R per load), and the ~30 extra
+  // instructions per pair cost more than the wavefronts: manix +5.7 % instead of +8.6 %,
+  // fbm 512^3 +31 % instead of +37 % over skip=0.)
+  if (SKIP && skip) kx = ky = kz = 0u;
+  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
+  F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
+  return skip;
+}
 template <int LAYOUT>
 CVR_DEV float density_at_grid(const MediumParams& m, const TrackInv& I, float cx, float cy, float cz) {
   CellFetch F;
@@ -266,35 +318,30 @@ CVR_DEV V3 albedo_cell8_fast(const MediumParams& m, V3 p) {
         cz = p.z * (float)(uint32_t)(m.anz - 1);
   float flx = floorf(cx), fly = floorf(cy), flz = floorf(cz);
   size_t kx = cell_index((int)flx, m.anx), ky = cell_index((int)fly, m.any), kz = cell_index((int)flz, m.anz);
-  const float4* A = m.acells + 8 * (kx + (size_t)(m.anx + 1) * (ky + (size_t)(m.any + 1) * kz));
-  float4 a[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = __ldg(A + i);
+  AlbedoCell a;
+  ldg_albedo_cell(m.acells + CVR_ACELL_FLOATS * (kx + (size_t)(m.anx + 1) * (ky + (size_t)(m.any + 1) * kz)), a);
   float fx = cx - flx, fy = cy - fly, fz = cz - flz;
-#if CVR_TRILERP_X2
-  // corners a[zyx]; each float4 is two aligned pairs (r,g) and (b,w)
-  const f32x2_t FX = pack2(fx, fx), FY = pack2(fy, fy), FZ = pack2(fz, fz);
-  f32x2_t rg[4], bw[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    rg[i] = lerp2(pack2(a[2 * i].x, a[2 * i].y), pack2(a[2 * i + 1].x, a[2 * i + 1].y), FX);
-    bw[i] = lerp2(pack2(a[2 * i].z, a[2 * i].w), pack2(a[2 * i + 1].z, a[2 * i + 1].w), FX);
-  }
-  f32x2_t rg0 = lerp2(rg[0], rg[1], FY), rg1 = lerp2(rg[2], rg[3], FY);
-  f32x2_t bw0 = lerp2(bw[0], bw[1], FY), bw1 = lerp2(bw[2], bw[3], FY);
   V3 out;
-  float w;
-  unpack2(lerp2(rg0, rg1, FZ), out.x, out.y);
-  unpack2(lerp2(bw0, bw1, FZ), out.z, w);
-  return out;
-#else
-  float r[8], g[8], b[8];
-  // trilerp_fast expects the density corner order (z fastest inside a pair)
-  const int perm[8] = {0, 4, 1, 5, 2, 6, 3, 7};
+#if CVR_TRILERP_X2
+  // (r, g) pairs of corner i = x | y << 1 | z << 2: x, y, z blends on packed pairs; b as a density cell
+  const f32x2_t FX = pack2(fx, fx), FY = pack2(fy, fy), FZ = pack2(fz, fz);
+  f32x2_t rg[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = a[perm[i]].x, g[i] = a[perm[i]].y, b[i] = a[perm[i]].z;
-  return v3(trilerp_fast(r, fx, fy, fz), trilerp_fast(g, fx, fy, fz), trilerp_fast(b, fx, fy, fz));
+  for (int i = 0; i < 4; ++i)
+    rg[i] = lerp2(pack2(a.rg[4 * i], a.rg[4 * i + 1]), pack2(a.rg[4 * i + 2], a.rg[4 * i + 3]), FX);
+  unpack2(lerp2(lerp2(rg[0], rg[1], FY), lerp2(rg[2], rg[3], FY), FZ), out.x, out.y);
+  out.z = trilerp_fast(a.b, fx, fy, fz);
+#else
+  float r[8], g[8];
+  // trilerp_fast expects the density corner order k = z | x << 1 | y << 2
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = ((k >> 1) & 1) | (((k >> 2) & 1) << 1) | ((k & 1) << 2);
+    r[k] = a.rg[2 * i], g[k] = a.rg[2 * i + 1];
+  }
+  out = v3(trilerp_fast(r, fx, fy, fz), trilerp_fast(g, fx, fy, fz), trilerp_fast(a.b, fx, fy, fz));
 #endif
+  return out;
 }
 // Same test, but the hit face comes out as the 0..5 normal code the slots store (0:+x 1:+y 2:+z
 // 3:-x 4:-y 5:-z) and `inside` from the sign of that one direction component, instead of a
@@ -547,18 +594,22 @@ CVR_DEV GridRay grid_ray(const TrackInv& I, const V3& o, const V3& d) {
   asm volatile("" : "+f"(G.g0x), "+f"(G.g0y), "+f"(G.g0z), "+f"(G.gdx), "+f"(G.gdy), "+f"(G.gdz));
   return G;
 }
-template <int LAYOUT, bool COUNT>
+template <int LAYOUT, bool COUNT, bool SKIP = false>
 CVR_DEV void track_step_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
-                             LaneCounters& C) {
+                             LaneCounters& C, const SkipTab& S = SkipTab()) {
   const float u = R.rng.next();
-  const float u2 = R.rng.next();
+  const uint32_t r2 = R.rng.next_u32();
+  const float u2 = r2 * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
   R.t = fmaf(lg2_fast(fmaxf(u, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
-  const float dens = density_at_grid<LAYOUT>(P.med, I, fmaf(R.t, G.gdx, G.g0x), fmaf(R.t, G.gdy, G.g0y),
-                                     fmaf(R.t, G.gdz, G.g0z));
+  CellFetch F;
+  const bool skipped = cell_fetch_skip<LAYOUT, SKIP>(P, I, S, fmaf(R.t, G.gdx, G.g0x), fmaf(R.t, G.gdy, G.g0y),
+                                                     fmaf(R.t, G.gdz, G.g0z), r2, F);
+  const float dens = trilerp_fast(F.v, F.fx, F.fy, F.fz);
   if (COUNT) ++C.dens;
+  if (COUNT && SKIP) C.skip += skipped ? 1u : 0u;
   // select form (no divergent branch): inside ? (accepted ? event : keep tracking) : parked boundary
   const bool inside = R.t <= R.dist;
-  const bool accepted = !(dens * I.sig_ratio < u2);
+  const bool accepted = !skipped && !(dens * I.sig_ratio < u2);
   const int ev = (R.t < R.dist) ? S_SCATTER : S_BOUNDARY;
   R.state = inside ? (accepted ? ev : S_TRACK) : S_BOUNDARY_P;
   R.t = inside ? R.t : u2;
@@ -572,17 +623,24 @@ CVR_DEV void track_step_fast(const KernelParams& P, const TrackInv& I, const Gri
 // counted as speculative and the generator is rolled back by two draws.  The state after 2
 // draws (v2,v3,v4,n1,n2) shares three words with the state after 4 (v4,n1,n2,n3,n4), so
 // the roll-back is six selects on two saved words, not an inverse computation.
-template <int LAYOUT, bool COUNT>
+template <int LAYOUT, bool COUNT, bool SKIP = false>
 CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<Xorwow>& R,
-                             LaneCounters& C) {
+                             LaneCounters& C, const SkipTab& S = SkipTab()) {
   Xorwow& g = R.rng;
   const uint32_t s2 = g.v2, s3 = g.v3;
-  const float u1 = g.next(), w1 = g.next(), u2 = g.next(), w2 = g.next();
+  const float u1 = g.next();
+  const uint32_t r1 = g.next_u32();
+  const float u2 = g.next();
+  const uint32_t r2 = g.next_u32();
+  // curand_uniform of the two accept words (Xorwow::next)
+  const float w1 = r1 * 2.3283064e-10f + (2.3283064e-10f / 2.0f), w2 = r2 * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
   const float t1 = fmaf(lg2_fast(fmaxf(u1, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
   const float t2 = fmaf(lg2_fast(fmaxf(u2, CVR_EPS)), I.neg_ln2_inv_sigmat, t1);
   CellFetch F1, F2;
-  cell_fetch<LAYOUT>(P.med, I, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y), fmaf(t1, G.gdz, G.g0z), F1);
-  cell_fetch<LAYOUT>(P.med, I, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y), fmaf(t2, G.gdz, G.g0z), F2);
+  const bool k1 = cell_fetch_skip<LAYOUT, SKIP>(P, I, S, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y),
+                                                fmaf(t1, G.gdz, G.g0z), r1, F1);
+  const bool k2 = cell_fetch_skip<LAYOUT, SKIP>(P, I, S, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y),
+                                                fmaf(t2, G.gdz, G.g0z), r2, F2);
   // both loads must be in flight before the first blend: tie the two results together so
   // that ptxas cannot consume load 1 (and reuse its registers) before load 2 is issued
   // (a REAL data dependency: an empty asm leaves nothing for ptxas to order; density values
@@ -592,7 +650,8 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   const float dens1 = trilerp_fast(F1.v, F1.fx, F1.fy, F1.fz);
   const float dens2 = trilerp_fast(F2.v, F2.fx, F2.fy, F2.fz);
   const bool in1 = t1 <= R.dist, in2 = t2 <= R.dist;
-  const bool acc1 = !(dens1 * I.sig_ratio < w1), acc2 = !(dens2 * I.sig_ratio < w2);
+  // a skipped step is a certain null collision (SkipTab): its blend is of an unrelated cell
+  const bool acc1 = !k1 && !(dens1 * I.sig_ratio < w1), acc2 = !k2 && !(dens2 * I.sig_ratio < w2);
   const bool cont1 = in1 && !acc1;  // step 1 was a null collision inside the medium
   // the step that decides this lane's fate
   const float td = cont1 ? t2 : t1, wd = cont1 ? w2 : w1;
@@ -610,6 +669,7 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   if (COUNT) {
     C.dens += cont1 ? 2u : 1u;
     C.spec += cont1 ? 0u : 1u;
+    if (SKIP) C.skip += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);  // cell loads not issued (of the 2 per pair, speculative one included)
   }
 }
 
@@ -832,6 +892,7 @@ CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lan
     C.alb += __shfl_xor_sync(FULL, C.alb, s);
     C.esc += __shfl_xor_sync(FULL, C.esc, s);
     C.spec += __shfl_xor_sync(FULL, C.spec, s);
+    C.skip += __shfl_xor_sync(FULL, C.skip, s);
   }
   if (lane == 0) {  // one atomic per warp per counter
     atomicAdd(&P.ctr->paths, (unsigned long long)C.paths);
@@ -840,6 +901,7 @@ CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lan
     atomicAdd(&P.ctr->albedo_lookups, (unsigned long long)C.alb);
     atomicAdd(&P.ctr->escaped, (unsigned long long)C.esc);
     if (C.spec) atomicAdd(&P.ctr->speculative, (unsigned long long)C.spec);
+    if (C.skip) atomicAdd(&P.ctr->skipped, (unsigned long long)C.skip);
   }
 }
 
@@ -1369,8 +1431,8 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 enum : uint32_t { K_TRACK = 0, K_SCATTER = 1, K_BOUNDARY = 2, K_IDLE = 3, K_DONE = 4, K_BUSY = 5 };
 
 // dynamic shared memory of k_volpt_warp for a CTA of `block` threads with W slots per warp
-inline size_t warp_sched_smem_bytes(int block, int W) {
-  return (size_t)(block / 32) * (W * (sizeof(PathSlot) + 1) + 32);
+inline size_t warp_sched_smem_bytes(int block, int W, size_t skip_table_bytes = 0) {
+  return (size_t)(block / 32) * (W * (sizeof(PathSlot) + 1) + 32) + skip_table_bytes;
 }
 
 // (Measured and rejected, twice: in-place refill of finished tracking lanes from waiting
@@ -1380,9 +1442,17 @@ inline size_t warp_sched_smem_bytes(int block, int W) {
 // (64: 145 KB of slots per SM at 28 warps, 96: 218 KB).  Measured on B200 (1024^2 x 16 spp,
 // Msamples/s, W = 64 / 96): hetvol 889 / 961, bucky 5031 / 5276 (volumes resident in L2:
 // fill wins), manix 2355 / 2102, fbm 512^3 1059 / 1031 (volumes beyond L2: L1 wins).
-template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64>
-__global__ void __launch_bounds__(CVR_WBLOCK, CVR_WMIN_BLOCKS)
+// SKIP = fetch-skip table (SkipTab above) in shared memory behind the slots.  It has to be ONE
+// table per SM to leave room for the slots, so these instantiations run as one CTA of
+// CVR_WSKIP_BLOCK = 896 threads per SM (the same 28 warps and 72 registers as 7 x 128; warps
+// never interact, the CTA only shares the table and one barrier after loading it).
+#ifndef CVR_WSKIP_BLOCK
+#define CVR_WSKIP_BLOCK 896
+#endif
+template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64, bool SKIP = false>
+__global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 : CVR_WMIN_BLOCKS)
     k_volpt_warp(const __grid_constant__ KernelParams P) {
+  static_assert(!SKIP || (FAST && !LOCAL && LAYOUT != LAYOUT_LINEAR), "the skip table belongs to the fused global-majorant loop");
   typedef Xorwow Rng;
   constexpr int K = W / 32;
   static_assert(W % 32 == 0 && K >= 1 && K <= 7, "slots per warp must be 32..224 in steps of 32");
@@ -1394,6 +1464,16 @@ __global__ void __launch_bounds__(CVR_WBLOCK, CVR_WMIN_BLOCKS)
   PathSlot* const slots = reinterpret_cast<PathSlot*>(s_raw) + warp * W;
   uint8_t* const keys = s_raw + (size_t)nw * W * sizeof(PathSlot) + warp * W;
   uint8_t* const list = s_raw + (size_t)nw * W * (sizeof(PathSlot) + 1) + warp * 32;
+  // SKIP kernels always run with CVR_WSKIP_BLOCK threads: the table offset is a compile-time constant
+  constexpr size_t kTabOffset = (size_t)(CVR_WSKIP_BLOCK / 32) * (W * (sizeof(PathSlot) + 1) + 32);
+  SkipTab ST;
+  ST.tab = s_raw + kTabOffset;
+  if (SKIP) {  // stage the table once per CTA
+    uint8_t* const tab = s_raw + kTabOffset;
+    for (uint32_t i = threadIdx.x * 4u; i < P.skip_n; i += blockDim.x * 4u)  // skip_n is padded to 4 bytes
+      *reinterpret_cast<uint32_t*>(tab + i) = __ldg(reinterpret_cast<const uint32_t*>(P.skip_tab + i));
+    __syncthreads();
+  }
 
   LaneCounters C;
   const unsigned long long per_tile = P.path_end - P.path_begin;
@@ -1433,6 +1513,12 @@ __global__ void __launch_bounds__(CVR_WBLOCK, CVR_WMIN_BLOCKS)
     if (c3 > best) best = c3, key = 3;
 
     // ---------------------------------------------------------------- pick <= 32 slots of that state
+    // (Measured and rejected: ranking the slots within their bank-residue class -- slot s has its
+    // 16-byte fields in bank group (5 s + k) mod 8, so a quarter-warp holding 8 different residues
+    // is conflict-free -- removes 67 % of the shared-memory bank conflicts and halves the
+    // long-scoreboard stall, but a class with fewer than 4 candidates leaves holes in the batch:
+    // +16 % instructions, hetvol 1098 -> 1012, bucky 5620 -> 5131 Msamples/s; restricted to states
+    // with >= 40 candidates it is neutral.)
     unsigned base = 0;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -1486,13 +1572,13 @@ __global__ void __launch_bounds__(CVR_WBLOCK, CVR_WMIN_BLOCKS)
         for (int it = 0; it < steps; it += 2) {
           const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
           if (trk == 0 || (it > 0 && __popc(trk) < min_lanes)) break;
-          if (R.state == S_TRACK) track_pair_fast<LAYOUT, COUNT>(P, I, G, R, C);
+          if (R.state == S_TRACK) track_pair_fast<LAYOUT, COUNT, SKIP>(P, I, G, R, C, ST);
         }
       } else {
         for (int it = 0; it < steps; ++it) {
           const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
           if (trk == 0 || (it > 0 && __popc(trk) < min_lanes)) break;
-          if (R.state == S_TRACK) track_step_fast<LAYOUT, COUNT>(P, I, G, R, C);
+          if (R.state == S_TRACK) track_step_fast<LAYOUT, COUNT, SKIP>(P, I, G, R, C, ST);
         }
       }
     } else {
@@ -1556,9 +1642,11 @@ __global__ void k_build_density_cells(const float* __restrict__ D, int nx, int n
 }
 
 __global__ void k_build_albedo_cells(const float4* __restrict__ A, int nx, int ny, int nz,
-                                     float4* __restrict__ cells) {
+                                     float* __restrict__ cells) {
   size_t ncell = (size_t)(nx + 1) * (ny + 1) * (nz + 1);
-  // 8 threads per cell: one corner each -> 128-byte coalesced stores
+  // 8 threads per cell, one corner each: (r, g) to floats 2 i, 2 i + 1 and b to 16 + its
+  // density-order index (AlbedoCell, cvr_device.cuh); the 96 bytes of a cell are written by one
+  // group of 8 consecutive lanes
   size_t nthr = ncell * 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nthr;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -1571,12 +1659,13 @@ __global__ void k_build_albedo_cells(const float4* __restrict__ A, int nx, int n
     size_t X = (corner & 1) ? cell_hi(kx, nx) : cell_lo(kx, nx);
     size_t Y = (corner & 2) ? cell_hi(ky, ny) : cell_lo(ky, ny);
     size_t Z = (corner & 4) ? cell_hi(kz, nz) : cell_lo(kz, nz);
-    cells[i] = A[X + (size_t)nx * (Y + (size_t)ny * Z)];
+    const float4 a = A[X + (size_t)nx * (Y + (size_t)ny * Z)];
+    float* cell = cells + c * CVR_ACELL_FLOATS;
+    *reinterpret_cast<float2*>(cell + 2 * corner) = make_float2(a.x, a.y);
+    cell[16 + (((corner >> 2) & 1) | ((corner & 1) << 1) | (((corner >> 1) & 1) << 2))] = a.z;
   }
 }
 
-// majorant brick grid over the cell8 density layout: max of every corner value of every
-// cell in the brick (so it bounds any trilinear lookup whose cell lies in the brick)
 __global__ void k_build_majorant(const float4* __restrict__ cells, int nx, int ny, int nz, uint32_t mx,
                                  uint32_t my, uint32_t mz, float* __restrict__ maj) {
   // one warp per brick, lanes stride over its cells
@@ -1613,6 +1702,24 @@ __global__ void k_build_majorant2(const float* __restrict__ maj, uint32_t mx, ui
 // ---------------------------------------------------------------- resolve (A16)
 // ImageBufferTransfer.cu:6-18 with UtilityFunctors::Scale (Utilities.h:6-15): every
 // float of the tile divided by `scale`, written at the tile origin of the image.
+// fetch-skip table (SkipTab): byte per brick of (8 << e)^3 cells from the 8^3-brick majorants
+__global__ void k_build_skip_table(const float* __restrict__ maj, uint32_t mx, uint32_t my, uint32_t mz, uint32_t e,
+                                   uint32_t bx, uint32_t by, uint32_t bz, float sig_ratio, uint8_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bx * by * bz) return;
+  const uint32_t X = i % bx, Y = (i / bx) % by, Z = i / (bx * by);
+  float m = 0.f;
+  for (uint32_t z = Z << e; z < min((Z + 1u) << e, mz); ++z)
+    for (uint32_t y = Y << e; y < min((Y + 1u) << e, my); ++y)
+      for (uint32_t x = X << e; x < min((X + 1u) << e, mx); ++x) m = fmaxf(m, maj[x + (size_t)mx * (y + (size_t)my * z)]);
+  // r = the largest value `density * sig_ratio` can take in the brick (same fp32 multiply as the loop)
+  const float r = m * sig_ratio;
+  float q = ceilf(r * 256.0f * 1.00001f);
+  q = !(q >= 1.0f) ? 1.0f : (q > 256.0f ? 256.0f : q);  // NaN / negative -> never more permissive than r = 1/256
+  if (!(r <= 1.0f)) q = 256.0f;                           // NaN or majorant above max_density: never skip
+  out[i] = (uint8_t)((int)q - 1);
+}
+
 __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w, uint32_t tile_h,
                                uint32_t in_stride, uint32_t in_off_x, uint32_t in_off_y,
                                float4* __restrict__ image, uint32_t full_w, uint32_t off_x,

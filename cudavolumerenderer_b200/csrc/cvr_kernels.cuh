@@ -155,6 +155,9 @@ struct PathRegs {
 
 struct LaneCounters {
   uint32_t paths = 0, bounces = 0, dens = 0, alb = 0, esc = 0, spec = 0, skip = 0;
+  // pair loop: iterations and iterations whose second step really happened; folded into
+  // dens (= pairs + cont) and spec (= pairs - cont) when the counters are flushed
+  uint32_t pairs = 0, cont = 0;
 };
 
 // Loop invariants of the Woodcock step (the reference recomputes them every
@@ -653,11 +656,16 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   // a skipped step is a certain null collision (SkipTab): its blend is of an unrelated cell
   const bool acc1 = !k1 && !(dens1 * I.sig_ratio < w1), acc2 = !k2 && !(dens2 * I.sig_ratio < w2);
   const bool cont1 = in1 && !acc1;  // step 1 was a null collision inside the medium
-  // the step that decides this lane's fate
+  // the step that decides this lane's fate: step 2 if step 1 continued, else step 1.  Its `inside`
+  // and `accepted` flags as pure predicate logic (a ?: between bools costs ptxas a SEL / LOP3 /
+  // ISETP round trip through an integer register each):
+  //   ind  = cont1 ? in2  : in1   = in1 && (acc1 || in2)
+  //   accd = cont1 ? acc2 : acc1  = acc1 || (cont1 && acc2)
   const float td = cont1 ? t2 : t1, wd = cont1 ? w2 : w1;
-  const bool ind = cont1 ? in2 : in1, accd = cont1 ? acc2 : acc1;
-  const int ev = (td < R.dist) ? S_SCATTER : S_BOUNDARY;
-  R.state = ind ? (accd ? ev : S_TRACK) : S_BOUNDARY_P;
+  const bool ind = in1 & (acc1 | in2), accd = acc1 | (cont1 & acc2);
+  int st = (td < R.dist) ? S_SCATTER : S_BOUNDARY;
+  st = accd ? st : S_TRACK;
+  R.state = ind ? st : S_BOUNDARY_P;
   R.t = ind ? td : wd;
   // roll the generator back by two draws when step 2 never happened
   g.v4 = cont1 ? g.v4 : g.v2;
@@ -667,8 +675,8 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   g.v0 = cont1 ? g.v0 : s2;
   g.d = cont1 ? g.d : g.d - 2u * 362437u;
   if (COUNT) {
-    C.dens += cont1 ? 2u : 1u;
-    C.spec += cont1 ? 0u : 1u;
+    C.pairs += 1u;
+    C.cont += cont1 ? 1u : 0u;
     if (SKIP) C.skip += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);  // cell loads not issued (of the 2 per pair, speculative one included)
   }
 }
@@ -885,6 +893,8 @@ template <bool COUNT>
 CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lane) {
   if (!COUNT) return;
   const unsigned FULL = 0xffffffffu;
+  C.dens += C.pairs + C.cont;
+  C.spec += C.pairs - C.cont;
   for (int s = 16; s > 0; s >>= 1) {
     C.paths += __shfl_xor_sync(FULL, C.paths, s);
     C.bounces += __shfl_xor_sync(FULL, C.bounces, s);
@@ -1569,9 +1579,12 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
       // few lanes left and other tracking paths of this warp waiting in slots: stop, they merge
       const int steps = P.track_steps, min_lanes = others_track ? P.track_min_lanes : 0;
       if (P.pair) {
+        // one test per iteration: stop below `need` tracking lanes; the first iteration runs with any
+        int need = 1;
         for (int it = 0; it < steps; it += 2) {
           const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE
-          if (trk == 0 || (it > 0 && __popc(trk) < min_lanes)) break;
+          if (__popc(trk) < need) break;
+          need = max(min_lanes, 1);
           if (R.state == S_TRACK) track_pair_fast<LAYOUT, COUNT, SKIP>(P, I, G, R, C, ST);
         }
       } else {

@@ -3,13 +3,13 @@
 set -x
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -x -q -m gpu > gpurun_out/c_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/c_tests.log
-tail -5 gpurun_out/c_tests.log
-timeout 600 python tools/ab_skip.py 1024 16 > gpurun_out/c_ab.log 2>&1; echo "ab rc=$?" >> gpurun_out/c_ab.log
-cat gpurun_out/c_ab.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -x -q -m gpu > gpurun_out/e_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/e_tests.log
+tail -5 gpurun_out/e_tests.log
+timeout 600 python tools/ab_skip.py 1024 16 > gpurun_out/e_ab.log 2>&1; echo "ab rc=$?" >> gpurun_out/e_ab.log
+cat gpurun_out/e_ab.log
 for s in 0; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_volpt_warp -s 1 -c 1 -f -o gpurun_out/c_hetvol_skip$s \
-    python tools/profile_run.py hetvol 512 16 2 skip=$s > gpurun_out/c_ncu_skip$s.log 2>&1
-  tail -2 gpurun_out/c_ncu_skip$s.log
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_volpt_warp -s 1 -c 1 -f -o gpurun_out/e_hetvol_skip$s \
+    python tools/profile_run.py hetvol 512 16 2 skip=$s > gpurun_out/e_ncu_skip$s.log 2>&1
+  tail -2 gpurun_out/e_ncu_skip$s.log
 done
-timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/c_bench.json 2> gpurun_out/c_bench.err; tail -c 3000 gpurun_out/c_bench.json
+timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/e_bench.json 2> gpurun_out/e_bench.err; tail -c 3000 gpurun_out/e_bench.json

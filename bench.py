@@ -261,6 +261,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # NCCL's own banner ("NCCL version ...") goes to stderr: stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)

@@ -1528,7 +1528,9 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     // is conflict-free -- removes 67 % of the shared-memory bank conflicts and halves the
     // long-scoreboard stall, but a class with fewer than 4 candidates leaves holes in the batch:
     // +16 % instructions, hetvol 1098 -> 1012, bucky 5620 -> 5131 Msamples/s; restricted to states
-    // with >= 40 candidates it is neutral.)
+    // with >= 40 candidates it is neutral; with a second pass that fills the holes with the
+    // left-over candidates through a temporary list only 36 % of the conflicts go and the extra
+    // ranking costs more than they did: hetvol 1210 -> 1174, bucky 5979 -> 5570.)
     unsigned base = 0;
 #pragma unroll
     for (int j = 0; j < K; ++j) {

@@ -36,8 +36,11 @@ for name, kernel, mk, res, spp, tiles, opts in CONFIGS:
            "msamples_per_s": c["paths"] / c["kernel_ms"] / 1e3, "density_lookups_per_s": c["density_lookups"] / c["kernel_ms"] * 1e3,
            "algorithmic_gb_per_s": alg / c["kernel_ms"] / 1e6, "lookups_per_path": c["density_lookups"] / c["paths"],
            "bounces_per_path": c["bounces"] / c["paths"], "speculative_lookups": c["speculative_lookups"],
+           "skipped_fetches": c["skipped_fetches"],
+           "fetched_fraction": 1.0 - c["skipped_fetches"] / max(c["density_lookups"] + c["speculative_lookups"], 1),
            "layout": info["layout"], "layout_gb": info["layout_bytes"] / 1e9, "image_mean": float(np.nanmean(img[..., :3])),
-           "options": {k: kl.getOption(k) for k in ("sched", "warp_slots", "pair", "tracking", "exact")}}
+           "options": {k: kl.getOption(k) for k in ("sched", "warp_slots", "pair", "tracking", "exact", "skip")},
+           "launch_shape": list(kl.launchShape())}
     out.append(row)
     print(json.dumps(row), flush=True)
     kl.close()

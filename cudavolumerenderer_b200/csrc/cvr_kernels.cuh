@@ -1581,7 +1581,10 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
       // few lanes left and other tracking paths of this warp waiting in slots: stop, they merge
       const int steps = P.track_steps, min_lanes = others_track ? P.track_min_lanes : 0;
       if (P.pair) {
-        // one test per iteration: stop below `need` tracking lanes; the first iteration runs with any
+        // one test per iteration: stop below `need` tracking lanes; the first iteration runs with any.
+        // (Two pairs per vote -- the census is 15 of the ~165 instructions of an iteration and runs
+        // with all 32 lanes -- was measured and rejected: the coarser exit costs more than the votes,
+        // bucky 5979 -> 5461, hetvol 1211 -> 1177, manix 2907 -> 2658 Msamples/s.)
         int need = 1;
         for (int it = 0; it < steps; it += 2) {
           const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);  // lanes without a path are S_DONE

@@ -261,11 +261,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # NCCL's own banner ("NCCL version ...") goes to stderr: stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its banner ("NCCL version ...") on stdout when the first communicator comes up;
+        # stdout carries the ONE JSON line, so file descriptor 1 points at stderr until NCCL is up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     sc = scenes.hetvol()
     total_spp = SPP * world

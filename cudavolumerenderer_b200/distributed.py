@@ -39,6 +39,15 @@ def render_sharded(launcher, res, n_tiles, iterations: int, mode: str, d_image, 
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     d_image.zero_()
+    if d_image.is_cuda:
+        # the zero fill is on torch's current stream; the render must not overtake it.  Ordered by
+        # the stream itself when the launcher was given that stream (setStream), by a host-side
+        # wait otherwise (the launcher's own stream is non-blocking).
+        import torch
+
+        cur = torch.cuda.current_stream(d_image.device)
+        if launcher.streamPtr() != (cur.cuda_stream or 1):
+            cur.synchronize()
     kw = dict(fov_x=fov_x, inv_view=inv_view, d_image=d_image.data_ptr(), host_image=None, fuse_tiles=fuse_tiles)
     if mode == "spp":
         first, count = spp_shard(iterations, rank, world)

@@ -168,7 +168,20 @@ class VolPTKernelLauncher:
         return buf.value.decode()
 
     def setStream(self, cuda_stream_ptr: int | None) -> None:
+        """cudaStream_t to launch on.  None = the handle's own (non-blocking) stream.  0 -- what
+        torch reports for its DEFAULT stream -- is passed on as cudaStreamLegacy (0x1): the C ABI
+        reads a NULL stream as "own stream", and work launched there would not be ordered with
+        torch operations on the default stream (a d_image.zero_() enqueued before the render could
+        execute after the tiles were resolved and wipe them)."""
+        if cuda_stream_ptr is not None and int(cuda_stream_ptr) == 0:
+            cuda_stream_ptr = 1  # cudaStreamLegacy
+        self._stream = cuda_stream_ptr
         self._ck(self._lib.cvr_set_stream(self._h, cuda_stream_ptr), "set_stream")
+
+    def streamPtr(self) -> int | None:
+        """The stream handle given to setStream (cudaStreamLegacy = 1 for the default stream), or
+        None while the handle launches on its own stream."""
+        return getattr(self, "_stream", None)
 
     # -- RenderKernelLauncher.h:31-51
     def setOutputPtr(self, d_output: int) -> None:

@@ -66,6 +66,7 @@ struct cvr_renderer {
   int track_min_lanes = 12;
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
   int fix_nan = 0;
+  int exit_others = 16;  // KernelParams::exit_others
   int skip = -1;  // fetch-skip table (cvr_kernels.cuh: SkipTab): -1 = auto (on where it applies), 0, 1
 
   // launcher state
@@ -529,6 +530,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.track_min_lanes = h->track_min_lanes;
   P.fix_nan = h->fix_nan;
   P.policy = h->policy;
+  P.exit_others = h->exit_others;
   P.pair = effective_pair(h);
   P.rr = h->rr;
   P.pullback = (h->variant != VAR_REGEN) ? 1 : 0;
@@ -739,6 +741,8 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     h->policy = atoi(value);
   } else if (k == "pair") {
     h->pair = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
+  } else if (k == "exit_others") {
+    h->exit_others = atoi(value);
   } else if (k == "skip") {
     h->skip = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
     h->inited = false;
@@ -797,6 +801,8 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(h->policy);
   else if (k == "pair")
     v = std::to_string(effective_pair(h));
+  else if (k == "exit_others")
+    v = std::to_string(h->exit_others);
   else if (k == "skip")  // "0" or the brick edge in cells the table was planned with (after the first launch / init)
     v = h->skip_bytes ? std::to_string(1u << h->skip_shift) : std::string(skip_wanted(h) && !h->inited ? "auto" : "0");
   else if (k == "warp_slots")

@@ -1007,60 +1007,62 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 // up to `track_steps` Woodcock steps, and store the paths back.  Each path's own
 // operation and RNG-draw order is unchanged; only which lane executes it changes.
 // =============================================================================
+// Field grouping by WHO writes: q0..q2 change only at events ("static"), q3 / q4 after every batch
+// ("dynamic": the generator, t and the state).  Every access is then a whole 16-byte vector: the
+// first grouping kept t in q0.w and the state in q2.w, so a tracking batch ended with two extra
+// scalar stores and began with a scalar and a 64-bit load -- with 80-byte slots a 32-bit access
+// of 32 lanes falls on 8 banks only, each about as expensive on the L1 data pipe as a full vector
+// (the pipe is the kernel's busiest unit).
 struct __align__(16) PathSlot {
-  float4 q0;  // o.xyz, t
-  float4 q1;  // d.xyz, dist
-  float4 q2;  // thr.xyz, meta (state | ncode << 3 | bounces << 6) as bits
+  float4 q0;  // o.xyz, dist
+  float4 q1;  // d.xyz, out_idx (bits)
+  float4 q2;  // thr.xyz, path_lo (bits)
   uint4 q3;   // rng v0..v3
-  uint4 q4;   // rng v4, d, out_idx, path_lo
+  uint4 q4;   // rng v4, d, t (bits), meta (state | ncode << 3 | bounces << 6)
 };
 
 CVR_DEV void slot_store(PathSlot& s, const PathRegs<Xorwow>& R) {
   uint32_t meta = (uint32_t)R.state | ((uint32_t)R.ncode << 3) | (R.bounces << 6);
-  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.t);
-  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, R.dist);
-  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, __uint_as_float(meta));
+  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.dist);
+  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, __uint_as_float(R.out_idx));
+  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, __uint_as_float(R.path_lo));
   s.q3 = make_uint4(R.rng.v0, R.rng.v1, R.rng.v2, R.rng.v3);
-  s.q4 = make_uint4(R.rng.v4, R.rng.d, R.out_idx, R.path_lo);
+  s.q4 = make_uint4(R.rng.v4, R.rng.d, __float_as_uint(R.t), meta);
 }
 CVR_DEV void slot_load(const PathSlot& s, PathRegs<Xorwow>& R) {
   float4 a = s.q0, b = s.q1, c = s.q2;
   uint4 e = s.q3, f = s.q4;
-  R.o = v3(a.x, a.y, a.z), R.t = a.w;
-  R.d = v3(b.x, b.y, b.z), R.dist = b.w;
-  R.thr_x = c.x, R.thr_y = c.y, R.thr_z = c.z;
-  uint32_t meta = __float_as_uint(c.w);
-  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
+  R.o = v3(a.x, a.y, a.z), R.dist = a.w;
+  R.d = v3(b.x, b.y, b.z), R.out_idx = __float_as_uint(b.w);
+  R.thr_x = c.x, R.thr_y = c.y, R.thr_z = c.z, R.path_lo = __float_as_uint(c.w);
   R.rng.v0 = e.x, R.rng.v1 = e.y, R.rng.v2 = e.z, R.rng.v3 = e.w;
-  R.rng.v4 = f.x, R.rng.d = f.y, R.out_idx = f.z, R.path_lo = f.w;
+  R.rng.v4 = f.x, R.rng.d = f.y, R.t = __uint_as_float(f.z);
+  const uint32_t meta = f.w;
+  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
 }
 
 // The tracking loop only changes t, the state and the generator; everything else is
 // written once after the event ("static" part) so that o, d, throughput and the output
-// index are dead registers inside the loop, and a pure tracking batch moves 56 + 32 bytes
-// per path through shared memory instead of 80 + 80.
+// index are dead registers inside the loop, and a pure tracking batch moves 64 + 32 bytes
+// per path through shared memory (4 vector loads, 2 vector stores) instead of 80 + 80.
 CVR_DEV void slot_load_track(const PathSlot& s, PathRegs<Xorwow>& R) {
   float4 a = s.q0, b = s.q1;
-  uint32_t meta = __float_as_uint(s.q2.w);
-  uint4 e = s.q3;
-  uint2 f = *reinterpret_cast<const uint2*>(&s.q4);
-  R.o = v3(a.x, a.y, a.z), R.t = a.w;
-  R.d = v3(b.x, b.y, b.z), R.dist = b.w;
-  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
+  uint4 e = s.q3, f = s.q4;
+  R.o = v3(a.x, a.y, a.z), R.dist = a.w;
+  R.d = v3(b.x, b.y, b.z);
   R.rng.v0 = e.x, R.rng.v1 = e.y, R.rng.v2 = e.z, R.rng.v3 = e.w;
-  R.rng.v4 = f.x, R.rng.d = f.y;
+  R.rng.v4 = f.x, R.rng.d = f.y, R.t = __uint_as_float(f.z);
+  const uint32_t meta = f.w;
+  R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
 }
 CVR_DEV void slot_store_static(PathSlot& s, const PathRegs<Xorwow>& R) {
-  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.t);
-  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, R.dist);
-  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, 0.f);
-  reinterpret_cast<uint2*>(&s.q4)[1] = make_uint2(R.out_idx, R.path_lo);
+  s.q0 = make_float4(R.o.x, R.o.y, R.o.z, R.dist);
+  s.q1 = make_float4(R.d.x, R.d.y, R.d.z, __uint_as_float(R.out_idx));
+  s.q2 = make_float4(R.thr_x, R.thr_y, R.thr_z, __uint_as_float(R.path_lo));
 }
 CVR_DEV void slot_store_dynamic(PathSlot& s, float t, uint32_t meta, const Xorwow& g) {
-  s.q0.w = t;
-  s.q2.w = __uint_as_float(meta);
   s.q3 = make_uint4(g.v0, g.v1, g.v2, g.v3);
-  reinterpret_cast<uint2*>(&s.q4)[0] = make_uint2(g.v4, g.d);
+  s.q4 = make_uint4(g.v4, g.d, __float_as_uint(t), meta);
 }
 
 CVR_DEV int sort_key(int state) {

@@ -419,7 +419,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "kernel": "regenerationSK", "rng": kl.getOption("rng"), "layout": kl.getOption("layout"),
                    "sched": kl.getOption("sched"), "arithmetic": "fused (exact=0)" if kl.getOption("exact") == "0" else "reference order (exact=1)",
                    "tracking": kl.getOption("tracking"), "warp_slots": kl.getOption("warp_slots"),
-                   "speculative_pair_step": kl.getOption("pair"),
+                   "speculative_pair_step": kl.getOption("pair"), "fetch_skip_table": kl.getOption("skip"),
+                   "exit_others": kl.getOption("exit_others"),
                    "sharding": "spp" if world > 1 else "none", "l2": "flushed between steps (256 MiB write)",
                    "image_mean": img_mean, "nan_pixels": nan_px},
         "clocks": clk.summary(),

@@ -197,3 +197,36 @@ def test_world_size_2_gloo_reduction(tmp_path):
     for mode in ("spp", "tiles"):
         assert np.allclose(outs[1][mode], outs[2][mode], atol=1e-6), mode
         assert outs[1][mode][..., 0].sum() > 0
+
+
+def test_fetch_skip_table_quantisation_is_conservative():
+    """The byte the fetch-skip table stores per brick (k_build_skip_table, cvr_kernels.cuh):
+    s = clamp(ceil(r * 256 * (1 + 1e-5)), 1, 256) - 1 with r = majorant * sig_ratio, and the kernel
+    skips a cell load when (word >> 24) > s.  Restated here in fp32 and checked exhaustively: whenever
+    the test fires, the accept draw w = word * 2^-32 + 2^-33 (curand_uniform) is strictly above
+    r * (1 + 4 ulp) -- the most a fused trilinear blend of corners <= majorant can reach -- so the
+    skipped step is a null collision for certain; s = 255 never skips; r > 1 or NaN never skips."""
+    f32 = np.float32
+
+    def table_byte(r):
+        r = f32(r)
+        q = np.ceil(f32(f32(r * f32(256.0)) * f32(1.00001)))
+        q = f32(1.0) if not (q >= 1.0) else (f32(256.0) if q > 256.0 else q)
+        if not (r <= f32(1.0)):
+            q = f32(256.0)
+        return int(q) - 1
+
+    rng = np.random.default_rng(7)
+    rs = np.concatenate([np.linspace(0, 1, 4097), (np.arange(257) / 256.0), (np.arange(1, 257) / 256.0) * (1 - 2e-7),
+                         rng.random(20000)]).astype(np.float32)
+    for r in rs:
+        s = table_byte(r)
+        assert 0 <= s <= 255
+        if s == 255:
+            continue  # top byte is at most 255: the test `top > 255` never fires
+        top = s + 1  # the smallest top byte that skips; w is smallest for word = top << 24
+        w_min = f32(f32(np.uint32(top << 24)) * f32(2.3283064e-10) + f32(1.1641532e-10))
+        bound = f32(r) * f32(1 + 4 * 1.1920929e-07)
+        assert w_min > bound, (float(r), s, float(w_min), float(bound))
+    assert table_byte(0.0) == 0 and table_byte(1.0) == 255 and table_byte(1.5) == 255 and table_byte(float("nan")) == 255
+    assert table_byte(0.5) == 128  # ceil(128.00128) - 1: one step of margin above an exactly representable r

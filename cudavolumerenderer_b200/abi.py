@@ -114,6 +114,7 @@ SYMBOLS = [
     ("cvr_tile_table", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p]),
     ("cvr_default_camera", C.c_int, [C.c_uint32, C.c_uint32, C.c_float, f32p, f32p]),
     ("cvr_trace_paths", C.c_int, [H, C.c_uint64, C.c_uint64, C.c_void_p]),
+    ("cvr_trace_paths_logged", C.c_int, [H, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]),
     ("cvr_rng_kat", C.c_int, [H, C.POINTER(C.c_int32), C.c_int, C.c_int, u32p, f32p]),
     ("cvr_debug_lookup", C.c_int, [H, f32p, C.c_int, f32p, f32p]),
     ("cvr_gather_roofline", C.c_int, [H, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -77,6 +77,8 @@ struct cvr_renderer {
   uint32_t seed = 0;
   uint32_t sample_first = 0, sample_count = 0;
   float4* d_out = nullptr;
+  uint2* trace_log = nullptr;  // cvr_trace_paths_logged: event log of the launch in flight
+  uint32_t trace_log_cap = 0;
 
   // device memory owned by the handle
   float* d_density = nullptr;
@@ -179,6 +181,7 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
     return nullptr;
   }
   if (layout == LAYOUT_BRICK) {  // sparse bricks: fused arithmetic only, global or local majorant
+    if (exact) return nullptr;   // never render exact=1 with fused arithmetic silently
 #define CVR_KB(R, LOCAL)                                                                              \
   if (rng_mode == R && tracking == LOCAL)                                                             \
     return count ? (kernel_fn)k_volpt_warp<R, LAYOUT_BRICK, true, true, LOCAL != 0, W>                  \
@@ -210,6 +213,17 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_CELL8)
   CVR_K(RNG_XORWOW_THREAD, LAYOUT_LINEAR)
 #undef CVR_K
+  return nullptr;
+}
+
+// instantiations with the per-path event log (cvr_trace_paths_logged): warp scheduler, per-path
+// XORWOW streams, global majorant, no skip table, 64 slots
+kernel_fn pick_logged_kernel(int layout, int exact) {
+  if (layout == LAYOUT_CELL8)
+    return exact ? (kernel_fn)k_volpt_warp<RNG_XORWOW_PATH, LAYOUT_CELL8, true, false, false, 64, false, true>
+                 : (kernel_fn)k_volpt_warp<RNG_XORWOW_PATH, LAYOUT_CELL8, true, true, false, 64, false, true>;
+  if (layout == LAYOUT_BRICK && !exact)
+    return (kernel_fn)k_volpt_warp<RNG_XORWOW_PATH, LAYOUT_BRICK, true, true, false, 64, false, true>;
   return nullptr;
 }
 
@@ -503,6 +517,7 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
            unsigned long long path_end) {
   if (!h->scene_set) return fail(h, "launch before cvr_set_scene");
   if (h->tile_w == 0 || h->tile_h == 0) return fail(h, "launch before cvr_set_resolution");
+  if (path_end < path_begin) return fail(h, "launch: empty or inverted path range [%llu, %llu)", path_begin, path_end);
   if (set_device(h)) return 1;
   if (ensure_allocated(h) || ensure_init(h)) return 1;
   KernelParams& P = h->P;
@@ -522,6 +537,8 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.out_stride = out_stride;
   P.out_full = out_full;
   P.per_path = per_path;
+  P.path_log = per_path ? h->trace_log : nullptr;  // the event log belongs to cvr_trace_paths_logged only
+  P.log_cap = h->trace_log_cap;
   P.head = h->d_head;
   P.ctr = h->d_ctr;
   P.max_bounces = h->max_bounces;
@@ -544,11 +561,27 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.skip_bxy = h->skip_dim[0] * h->skip_dim[1];
   kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h),
                             h->skip_bytes != 0);
+  int grid = h->grid, block = effective_block(h);
+  size_t smem = h->smem_bytes;
+  if (P.path_log) {
+    // cvr_trace_paths_logged: the instantiation that keeps the event log (same estimator blocks,
+    // same arithmetic mode; 64 slots per warp, no skip table -- neither changes any path)
+    k = pick_logged_kernel(h->scene_layout, h->exact);
+    if (!k) return fail(h, "cvr_trace_paths_logged: no logging kernel for layout=%d exact=%d", h->scene_layout, h->exact);
+    block = CVR_WBLOCK;
+    smem = warp_sched_smem_bytes(block, 64, 0);
+    P.skip_tab = nullptr, P.skip_n = 0;
+    CVR_CUDA(h, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CVR_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, block, smem));
+    if (per_sm < 1) return fail(h, "cvr_trace_paths_logged: the logging kernel does not fit an SM");
+    grid = per_sm * h->sm_count;
+  }
   cudaEvent_t e0, e1;
   CVR_CUDA(h, cudaEventCreate(&e0));
   CVR_CUDA(h, cudaEventCreate(&e1));
   CVR_CUDA(h, cudaEventRecord(e0, h->stream));
-  k<<<h->grid, effective_block(h), h->smem_bytes, h->stream>>>(P);
+  k<<<grid, block, smem, h->stream>>>(P);
   CVR_CUDA(h, cudaGetLastError());
   CVR_CUDA(h, cudaEventRecord(e1, h->stream));
   h->timing.emplace_back(e0, e1);
@@ -557,12 +590,25 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   return 0;
 }
 
+// a sample range outside the iteration count is a caller bug, not something to clamp silently
+int check_sample_range(cvr_handle h) {
+  if (h->sample_first == 0 && h->sample_count == 0) return 0;
+  if (h->sample_first >= h->iterations)
+    return fail(h, "sample range: first sample %u is not below the iteration count %u", h->sample_first, h->iterations);
+  if ((unsigned long long)h->sample_first + h->sample_count > (unsigned long long)h->iterations)
+    return fail(h, "sample range: samples [%u, %llu) exceed the iteration count %u", h->sample_first,
+                (unsigned long long)h->sample_first + h->sample_count, h->iterations);
+  return 0;
+}
+
 void path_range(cvr_handle h, unsigned long long& b, unsigned long long& e) {
-  unsigned long long npix = (unsigned long long)(uint32_t)(h->P.cam.res_x * h->P.cam.res_y);
-  uint32_t first = h->sample_first;
-  uint32_t count = h->sample_count ? h->sample_count : (h->iterations - first);
-  if (first > h->iterations) first = h->iterations;
-  if (first + count > h->iterations) count = h->iterations - first;
+  // 64-bit throughout: first is clamped to the iteration count, the count to what is left of it
+  // (a bad range must never give path_end < path_begin: the persistent kernels' `per_tile` is unsigned)
+  const unsigned long long npix = (unsigned long long)(uint32_t)(h->P.cam.res_x * h->P.cam.res_y);
+  const unsigned long long iters = h->iterations;
+  const unsigned long long first = std::min<unsigned long long>(h->sample_first, iters);
+  const unsigned long long left = iters - first;
+  const unsigned long long count = h->sample_count ? std::min<unsigned long long>(h->sample_count, left) : left;
   b = npix * first;
   e = npix * (first + count);
 }
@@ -905,6 +951,11 @@ int cvr_set_scene(cvr_handle h, const cvr_scene_desc* s) {
     h->d_density = nullptr;
     h->d_albedo = nullptr;
   }
+  else {
+    // layout=linear: the H2D copies above are asynchronous for pinned host buffers, and the host
+    // pointers are borrowed for the duration of this call only
+    CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   pt.mark("free staging");
   m.density = h->d_density;
   m.dcells = h->d_dcells;
@@ -1165,6 +1216,8 @@ int cvr_get_seed(cvr_handle h, uint32_t* seed) {
 
 int cvr_set_sample_range(cvr_handle h, uint32_t first, uint32_t count) {
   CVR_CHECK_HANDLE(h);
+  // (0, 0) = every sample.  The range is checked against the iteration count when a render is
+  // launched (the setters may come in any order): check_sample_range
   h->sample_first = first, h->sample_count = count;
   return 0;
 }
@@ -1185,6 +1238,7 @@ int cvr_allocate(cvr_handle h) {
 int cvr_launch_render(cvr_handle h) {
   CVR_CHECK_HANDLE(h);
   if (!h->d_out) return fail(h, "cvr_launch_render before cvr_set_output");
+  if (check_sample_range(h)) return 1;
   unsigned long long b, e;
   path_range(h, b, e);
   // naiveSK seeds with the bare path id (NaiveVolPTsk_kernel.cuh:22, Q7)
@@ -1319,6 +1373,7 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
   cvr_set_iterations(h, r->iterations);
   cvr_set_inv_view_matrix(h, inv_view);
   cvr_set_sample_range(h, r->sample_first, r->sample_count);
+  if (check_sample_range(h)) return 1;
 
   const size_t image_px = (size_t)r->res_x * r->res_y;
   const size_t tile_px = (size_t)tile_dim[0] * tile_dim[1];
@@ -1415,6 +1470,22 @@ int cvr_trace_paths(cvr_handle h, uint64_t first, uint64_t count, void* d_per_pa
   uint32_t seed = h->variant == VAR_NAIVE ? 0u : h->seed;
   return launch(h, nullptr, h->tile_w, 0, nullptr, 1, 0, 0, seed, 0, (float4*)d_per_path, first,
                 first + count);
+}
+
+int cvr_trace_paths_logged(cvr_handle h, uint64_t first, uint64_t count, void* d_per_path, void* d_log, uint32_t log_cap) {
+  CVR_CHECK_HANDLE(h);
+  if (!d_per_path || !count) return fail(h, "cvr_trace_paths_logged: null buffer / zero count");
+  if (!d_log || !log_cap) return fail(h, "cvr_trace_paths_logged: null log / zero capacity");
+  if (h->rng_mode != RNG_XORWOW_PATH || h->sched != 3 || h->tracking != 0)
+    return fail(h, "cvr_trace_paths_logged: needs rng=xorwow-path, sched=warp, tracking=global");
+  if (set_device(h)) return 1;
+  CVR_CUDA(h, cudaMemsetAsync(d_per_path, 0, count * sizeof(float4), h->stream));
+  CVR_CUDA(h, cudaMemsetAsync(d_log, 0, count * (size_t)log_cap * sizeof(uint2), h->stream));
+  h->trace_log = (uint2*)d_log, h->trace_log_cap = log_cap;
+  uint32_t seed = h->variant == VAR_NAIVE ? 0u : h->seed;
+  int rc = launch(h, nullptr, h->tile_w, 0, nullptr, 1, 0, 0, seed, 0, (float4*)d_per_path, first, first + count);
+  h->trace_log = nullptr, h->trace_log_cap = 0;
+  return rc;
 }
 
 int cvr_rng_kat(cvr_handle h, const int32_t* seeds, int n_seeds, int n, uint32_t* words, float* uniforms) {

@@ -78,6 +78,8 @@ struct KernelParams {
   uint32_t out_stride;  // row stride in pixels
   int out_full;         // 0: index by tile-local pixel, 1: by full-image pixel (fused)
   float4* per_path;     // debug: per-path radiance (or nullptr)
+  uint2* path_log;      // debug: per-path event log, log_cap entries of (code, draw counter) per path (or nullptr)
+  uint32_t log_cap;
   unsigned long long* head;  // path queue head
   DeviceCounters* ctr;
   uint32_t max_bounces;
@@ -478,6 +480,18 @@ CVR_DEV V3 hg_sample_fast(V3 dir, float g, float e1, float e2) {
   return sin_theta * cp * v1 + sin_theta * sp * v2 + cos_theta * dir;
 }
 
+// ---- per-path event log (parity hook, cvr_trace_paths with a log buffer) -------------------
+// One entry per loop iteration of the path that ended in a scatter or boundary event, plus the
+// final escape: (code, XORWOW draw counter `d` when the event starts), the same record the CPU oracle
+// of the test suite keeps, so that a test can show where a path whose radiance differs from the CPU oracle's
+// left the common event prefix.
+enum : uint32_t { EV_SCATTER = 1, EV_BOUNDARY = 2, EV_ESCAPE = 3, EVF_OK = 16, EVF_WO_NEG = 32, EVF_WI_NEG = 64, EVF_KILLED = 128 };
+CVR_DEV uint32_t draw_tag(const Xorwow& g) { return g.d; }
+CVR_DEV uint32_t draw_tag(const Philox& g) { return g.c0 * 4u - g.have; }
+CVR_DEV void log_path_event(const KernelParams& P, uint32_t path_lo, uint32_t index, uint32_t code, uint32_t tag) {
+  if (index < P.log_cap) P.path_log[(size_t)path_lo * P.log_cap + index] = make_uint2(code, tag);
+}
+
 // ---- regeneration: camera ray for launch-global work item g (A1/A2 prologue) ----
 template <int RNGM, class Rng>
 CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned long long per_tile,
@@ -515,7 +529,7 @@ CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned lo
 }
 
 // ---- intersect (A5) + escape accumulation (A13) ----
-template <bool COUNT, bool FAST = false, class Rng>
+template <bool COUNT, bool FAST = false, bool LOG = false, class Rng>
 CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
   if (COUNT) ++C.bounces;
   bool inside, hit;
@@ -533,6 +547,7 @@ CVR_DEV void do_isect(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) 
     // the reference lets a NaN throughput through (u == 1.0 in sampleVisible11)
     const bool keep = !P.fix_nan || (fabsf(rx) <= 3.0e38f && fabsf(ry) <= 3.0e38f && fabsf(rz) <= 3.0e38f);
     if (P.per_path) P.per_path[R.path_lo] = make_float4(rx, ry, rz, 1.f);
+    if (LOG && P.path_log) log_path_event(P, R.path_lo, R.bounces, EV_ESCAPE, draw_tag(R.rng));
     if (P.out && keep) {
       float4* px = P.out + R.out_idx;
       atomicAdd(&px->x, rx);
@@ -824,8 +839,9 @@ CVR_DEV void do_roulette(const KernelParams& P, PathRegs<Rng>& R, Draw& rng) {
 }
 
 // ---- scatter event (A8, A9): NaiveVolPTsk_kernel.cuh:67-71 / Regeneration...:212-216 ----
-template <int LAYOUT, bool COUNT, bool FAST = false, class Rng>
+template <int LAYOUT, bool COUNT, bool FAST = false, bool LOG = false, class Rng>
 CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C) {
+  const uint32_t ev_tag = LOG ? draw_tag(R.rng) : 0u, ev_index = R.bounces;
   if (P.pullback)
     R.o = R.o + R.d * R.t - R.d * CVR_EPS;
   else
@@ -845,13 +861,18 @@ CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C
   float e2 = R.rng.next();
   R.d = FAST ? hg_sample_fast(R.d, P.med.hg_g, e1, e2) : hg_sample(R.d, P.med.hg_g, e1, e2);
   do_roulette<FAST>(P, R, R.rng);
+  if (LOG && P.path_log)
+    log_path_event(P, R.path_lo, ev_index, EV_SCATTER | (R.state == S_IDLE && P.rr ? EVF_KILLED : 0u), ev_tag);
 }
 
 // ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
-template <bool FAST = false, class Rng>
+template <bool FAST = false, bool LOG = false, class Rng>
 CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
   // S_BOUNDARY_P: the first uniform of this event was drawn by the tracking loop (parked in t)
   StashRng<Rng> rng{R.rng, R.t, R.state == S_BOUNDARY_P};
+  // the parked uniform was drawn ahead of the event: it does not count as consumed yet
+  const uint32_t ev_tag = LOG ? draw_tag(R.rng) - (rng.has ? 362437u : 0u) : 0u, ev_index = R.bounces;
+  uint32_t ev_code = EV_BOUNDARY;
   float weight = 1;
   if (FAST) {
     const V3 dir = frame_to_local(R.ncode, normalize(v3(-R.d.x, -R.d.y, -R.d.z)));
@@ -869,10 +890,14 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
 #else
     if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
 #endif
+      ev_code |= EVF_OK | (R.d.z < 0.f ? EVF_WO_NEG : 0u);
       R.thr_x *= weight, R.thr_y *= weight, R.thr_z *= weight;
       R.d = frame_to_world(R.ncode, R.d);
       R.o = v3(fmaf(R.d.x, CVR_EPS, R.o.x), fmaf(R.d.y, CVR_EPS, R.o.y), fmaf(R.d.z, CVR_EPS, R.o.z));
+    } else {
+      ev_code |= R.d.z < 0.f ? EVF_WO_NEG : 0u;
     }
+    ev_code |= dir.z < 0.f ? EVF_WI_NEG : 0u;
   } else {
     Frame frame;
     frame.from_z(normal_from_code(R.ncode));
@@ -880,12 +905,17 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
     R.o = R.o + R.d * R.dist;
     // the sampler writes the LOCAL direction into the ray even when it then fails
     if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
+      ev_code |= EVF_OK | (R.d.z < 0.f ? EVF_WO_NEG : 0u);
       R.thr_x *= weight, R.thr_y *= weight, R.thr_z *= weight;
       R.d = frame.to_world(R.d);
       R.o = R.o + R.d * CVR_EPS;
+    } else {
+      ev_code |= R.d.z < 0.f ? EVF_WO_NEG : 0u;
     }
+    ev_code |= dir.z < 0.f ? EVF_WI_NEG : 0u;
   }
   do_roulette<FAST>(P, R, rng);
+  if (LOG && P.path_log) log_path_event(P, R.path_lo, ev_index, ev_code | (R.state == S_IDLE && P.rr ? EVF_KILLED : 0u), ev_tag);
   // nobody drew (grazing hit with roulette off): give the parked uniform back to the stream
   if (rng.has) R.rng.undo();
 }
@@ -1462,7 +1492,10 @@ inline size_t warp_sched_smem_bytes(int block, int W, size_t skip_table_bytes = 
 #ifndef CVR_WSKIP_BLOCK
 #define CVR_WSKIP_BLOCK 896
 #endif
-template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64, bool SKIP = false>
+// LOG = the per-path event log of cvr_trace_paths_logged (parity hook; its own instantiations, so
+// that the product kernels carry no trace of it: with a run-time test alone ptxas spilled 16-38
+// bytes in the event code of the 72-register kernels)
+template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W = 64, bool SKIP = false, bool LOG = false>
 __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 : CVR_WMIN_BLOCKS)
     k_volpt_warp(const __grid_constant__ KernelParams P) {
   static_assert(!SKIP || (FAST && !LOCAL && LAYOUT != LAYOUT_LINEAR), "the skip table belongs to the fused global-majorant loop");
@@ -1566,11 +1599,11 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
       unsigned idle = __ballot_sync(FULL, have && R.state == S_IDLE);
       if (idle) warp_regenerate<RNGM, COUNT>(P, idle, lane, total, per_tile, exhausted, R, C);
     } else if (key == 1) {
-      if (have) do_scatter<LAYOUT, COUNT, FAST>(P, R, C);
+      if (have) do_scatter<LAYOUT, COUNT, FAST, LOG>(P, R, C);
     } else if (key == 2) {
-      if (have) do_boundary<FAST>(P, R);
+      if (have) do_boundary<FAST, LOG>(P, R);
     }
-    if (have && R.state == S_ISECT) do_isect<COUNT, FAST>(P, R, C);
+    if (have && R.state == S_ISECT) do_isect<COUNT, FAST, LOG>(P, R, C);
     // everything the tracking loop does not touch goes back to the slot now
     if (key != 0 && have) slot_store_static(slots[slot], R);
     const uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);

@@ -10,6 +10,8 @@
 
 #include <cmath>
 #include <memory>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "RenderKernelLauncher.h"
@@ -53,6 +55,8 @@ inline void cuda_ck(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+typedef std::vector<std::pair<std::string, std::string>> LauncherOptions;
+
 template <class VolPathKernelLauncher>
 class CudaVolPath : public AbstractProgressiveRenderer {
   TilingConfig tiling_config_;
@@ -77,8 +81,12 @@ class CudaVolPath : public AbstractProgressiveRenderer {
   }
 
  public:
-  CudaVolPath(const Scene& scene, TilingConfig tiling, uint32_t iterations, int device = 0)
+  // `options` = key/value pairs for cvr_set_option, applied right after the launcher exists and
+  // BEFORE init() / setScene() (layout, sched, rng ... select the kernel and the device layout)
+  CudaVolPath(const Scene& scene, TilingConfig tiling, uint32_t iterations, int device = 0,
+              const LauncherOptions& options = {})
       : tiling_config_(tiling), iterations_(iterations), scene_(scene), kernel_launcher_(device) {
+    for (const auto& kv : options) kernel_launcher_.setOption(kv.first, kv.second);
     // constructor order of CudaVolPath.cpp:31-59
     initTileArray();
     auto rtv = scene_.getCamera()->getRasterToView();
@@ -147,12 +155,12 @@ class CudaVolPath : public AbstractProgressiveRenderer {
 // RendererFactory::createRenderer (RendererFactory.h:13-22,37-115): kernel name -> renderer
 inline std::unique_ptr<AbstractProgressiveRenderer> createRenderer(const std::string& kernel, const Scene& scene,
                                                                    TilingConfig tiling, uint32_t iterations,
-                                                                   int device = 0) {
-  if (kernel == "naiveSK") return std::make_unique<CudaVolPath<NaiveVolPTsk>>(scene, tiling, iterations, device);
-  if (kernel == "regenerationSK") return std::make_unique<CudaVolPath<RegenerationVolPTsk>>(scene, tiling, iterations, device);
-  if (kernel == "streamingSK") return std::make_unique<CudaVolPath<StreamingVolPTsk>>(scene, tiling, iterations, device);
-  if (kernel == "streamingMK") return std::make_unique<CudaVolPath<StreamingVolPTmk>>(scene, tiling, iterations, device);
-  if (kernel == "sortingSK") return std::make_unique<CudaVolPath<SortingVolPTsk>>(scene, tiling, iterations, device);
+                                                                   int device = 0, const LauncherOptions& options = {}) {
+  if (kernel == "naiveSK") return std::make_unique<CudaVolPath<NaiveVolPTsk>>(scene, tiling, iterations, device, options);
+  if (kernel == "regenerationSK") return std::make_unique<CudaVolPath<RegenerationVolPTsk>>(scene, tiling, iterations, device, options);
+  if (kernel == "streamingSK") return std::make_unique<CudaVolPath<StreamingVolPTsk>>(scene, tiling, iterations, device, options);
+  if (kernel == "streamingMK") return std::make_unique<CudaVolPath<StreamingVolPTmk>>(scene, tiling, iterations, device, options);
+  if (kernel == "sortingSK") return std::make_unique<CudaVolPath<SortingVolPTsk>>(scene, tiling, iterations, device, options);
   throw std::runtime_error("kernel '" + kernel + "' is not available in this build (naiveSK | regenerationSK | streamingSK | streamingMK | sortingSK)");
 }
 

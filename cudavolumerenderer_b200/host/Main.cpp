@@ -203,20 +203,8 @@ int runTest(const Options& o, const Scene& scene) {
     cuda_ck(cudaSetDevice(o.device), "cudaSetDevice");
     cuda_ck(cudaHostAlloc((void**)&pixels, npx * 16, cudaHostAllocWriteCombined), "cudaHostAlloc");
     std::fill(pixels, pixels + npx * 4, 0.f);
-    auto renderer = createRenderer(o.kernel, scene, tiling, o.iterations, o.device);
-    if (!o.lib_options.empty()) {
-      // options reach the launcher through the C ABI
-      if (auto* r = dynamic_cast<CudaVolPath<NaiveVolPTsk>*>(renderer.get()))
-        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
-      if (auto* r = dynamic_cast<CudaVolPath<RegenerationVolPTsk>*>(renderer.get()))
-        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
-      if (auto* r = dynamic_cast<CudaVolPath<StreamingVolPTsk>*>(renderer.get()))
-        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
-      if (auto* r = dynamic_cast<CudaVolPath<StreamingVolPTmk>*>(renderer.get()))
-        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
-      if (auto* r = dynamic_cast<CudaVolPath<SortingVolPTsk>*>(renderer.get()))
-        for (auto& kv : o.lib_options) r->launcher().setOption(kv.first, kv.second);
-    }
+    // --option pairs reach the launcher through the C ABI before init() / setScene()
+    auto renderer = createRenderer(o.kernel, scene, tiling, o.iterations, o.device, o.lib_options);
     auto t1 = std::chrono::steady_clock::now();
     printf("initialization time : %.2f sec \n", std::chrono::duration<float>(t1 - t0).count());
     Buffer2D out = make_buffer2D_float4(pixels, o.resolution[0], o.resolution[1]);

@@ -24,6 +24,15 @@ class RenderKernelLauncher {
  public:
   RenderKernelLauncher(const char* kernel, int device) {
     if (cvr_create(kernel, device, &h_)) throw std::runtime_error(std::string("cvr_create: ") + cvr_last_error(nullptr));
+    // The reference launches on the default stream and its caller clears / copies the tile buffer
+    // with plain cudaMemset / cudaMemcpy2D (CudaVolPath.cpp:196-207): keep that ordering.  The
+    // handle's own stream is non-blocking and would NOT order against those calls (a memset could
+    // still be zeroing the tile while the next launch accumulates into it).
+    if (cvr_set_stream(h_, (void*)0x1 /* cudaStreamLegacy */)) {
+      std::string msg = std::string("cvr_set_stream: ") + cvr_last_error(h_);
+      cvr_destroy(h_);
+      throw std::runtime_error(msg);
+    }
   }
   virtual ~RenderKernelLauncher() { cvr_destroy(h_); }
   RenderKernelLauncher(const RenderKernelLauncher&) = delete;

@@ -312,6 +312,10 @@ class VolPTKernelLauncher:
     def tracePaths(self, first: int, count: int, d_per_path: int) -> None:
         self._ck(self._lib.cvr_trace_paths(self._h, first, count, d_per_path), "tracePaths")
 
+    def tracePathsLogged(self, first: int, count: int, d_per_path: int, d_log: int, log_cap: int) -> None:
+        """tracePaths plus the per-path event log (DEVICE uint2[count * log_cap], include/cvr_abi.h)."""
+        self._ck(self._lib.cvr_trace_paths_logged(self._h, first, count, d_per_path, d_log, log_cap), "tracePathsLogged")
+
     def rngKat(self, seeds, n: int):
         seeds = np.ascontiguousarray(seeds, np.int32)
         w = np.zeros((len(seeds), n), np.uint32)

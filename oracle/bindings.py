@@ -54,6 +54,20 @@ class Counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class Trace(C.Structure):
+    """cvro_trace (cvr_oracle.h): event / decision log of one path."""
+    _fields_ = [("d0", C.c_uint32), ("n_events", C.c_uint32), ("cap_events", C.c_uint32),
+                ("ev_code", u32p), ("ev_d", u32p),
+                ("n_dec", C.c_uint32), ("cap_dec", C.c_uint32),
+                ("dec_kind", u32p), ("dec_d", u32p), ("dec_a", f32p), ("dec_b", f32p)]
+
+
+EV_SCATTER, EV_BOUNDARY, EV_ESCAPE = 1, 2, 3
+EVF_OK, EVF_WO_NEG, EVF_WI_NEG, EVF_KILLED = 16, 32, 64, 128
+DEC_EXIT, DEC_ACCEPT, DEC_ROULETTE, DEC_FRESNEL = 1, 2, 3, 4
+XORWOW_D_STEP = 362437  # the draw counter `d` advances by this per draw
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is mounted)."""
     if force or not os.path.exists(ORACLE_SO) or (
@@ -86,6 +100,12 @@ def lib() -> C.CDLL:
         L.cvro_trace_paths_naive.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_uint64,
                                              C.c_uint64, f32p, C.c_int, C.POINTER(Counters)]
         L.cvro_trace_paths_naive.restype = None
+        L.cvro_trace_paths_seeded.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_uint64, C.c_uint64,
+                                              C.c_uint32, C.c_int, f32p, C.c_int, C.POINTER(Counters)]
+        L.cvro_trace_paths_seeded.restype = None
+        L.cvro_trace_path_logged.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_int32, C.c_uint32, C.c_int,
+                                             C.c_uint32, f32p, C.POINTER(Trace)]
+        L.cvro_trace_path_logged.restype = C.c_int
         L.cvro_render_regen.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_uint32,
                                         C.c_uint32, C.c_int, C.c_uint32, f32p, C.c_int,
                                         C.POINTER(Counters)]
@@ -304,6 +324,37 @@ def trace_paths_naive(scene: Scene, cam: Camera, first: int, count: int, n_threa
     lib().cvro_trace_paths_naive(C.byref(scene), C.byref(cam), first, count, fp(out),
                                  n_threads or os.cpu_count() or 1, C.byref(ctr))
     return out, ctr.as_dict()
+
+
+def trace_paths_seeded(scene: Scene, cam: Camera, first: int, count: int, seed: int, variant: int = 0,
+                       n_threads: int | None = None):
+    """Per-path radiances with Rng(seed + path id); variant 0 = naive (scatter pull-back), 1 = regeneration."""
+    out = np.zeros((count, 4), np.float32)
+    ctr = Counters()
+    lib().cvro_trace_paths_seeded(C.byref(scene), C.byref(cam), first, count, seed & 0xffffffff, variant, fp(out),
+                                  n_threads or os.cpu_count() or 1, C.byref(ctr))
+    return out, ctr.as_dict()
+
+
+def trace_path_logged(scene: Scene, cam: Camera, rng_seed: int, image_id: int, variant: int = 0,
+                      cap_events: int = 4096, cap_dec: int = 1 << 18) -> dict:
+    """One path with its event and decision log (cvro_trace_path_logged).  rng_seed is the
+    int32 the generator is seeded with (path id + stream base, wrapped)."""
+    ev_code, ev_d = np.zeros(cap_events, np.uint32), np.zeros(cap_events, np.uint32)
+    dk, dd = np.zeros(cap_dec, np.uint32), np.zeros(cap_dec, np.uint32)
+    da, db = np.zeros(cap_dec, np.float32), np.zeros(cap_dec, np.float32)
+    t = Trace()
+    t.cap_events, t.cap_dec = cap_events, cap_dec
+    t.ev_code, t.ev_d = ev_code.ctypes.data_as(u32p), ev_d.ctypes.data_as(u32p)
+    t.dec_kind, t.dec_d = dk.ctypes.data_as(u32p), dd.ctypes.data_as(u32p)
+    t.dec_a, t.dec_b = fp(da), fp(db)
+    rad = np.zeros(3, np.float32)
+    seed32 = ((int(rng_seed) + 2 ** 31) % 2 ** 32) - 2 ** 31
+    esc = lib().cvro_trace_path_logged(C.byref(scene), C.byref(cam), seed32, image_id, variant, 0, fp(rad), C.byref(t))
+    ne, nd = min(t.n_events, cap_events), min(t.n_dec, cap_dec)
+    return {"escaped": bool(esc), "radiance": rad, "d0": int(t.d0), "n_events": int(t.n_events), "n_dec": int(t.n_dec),
+            "ev_code": ev_code[:ne].copy(), "ev_d": ev_d[:ne].copy(), "dec_kind": dk[:nd].copy(), "dec_d": dd[:nd].copy(),
+            "dec_a": da[:nd].copy(), "dec_b": db[:nd].copy()}
 
 
 def render_regen(scene: Scene, cam: Camera, iterations: int, seed: int = 0, rng_mode: int = 1,

@@ -22,6 +22,8 @@ typedef struct {
 } v3;
 
 /* ---- float3 helpers with the expression shapes of helper_math.h ---- */
+static void log_decision(uint32_t kind, float a, float b); /* optional path log, defined below */
+static void log_event(uint32_t code, uint32_t d);
 static inline v3 V(float x, float y, float z) {
   v3 r = {x, y, z};
   return r;
@@ -428,6 +430,7 @@ int cvro_ggx_sample(const float alpha[2], float eta, const float wi_in[3],
   float whdotwi = vdot(wh, wi);
   float F = cvro_fresnel_dielectric(eta, whdotwi, &whdotwt);
   *n_used = 3;
+  log_decision(CVRO_DEC_FRESNEL, u[2], F);
   if (u[2] <= F) {
     /* reflect (GGX.h:40-43): 2*c*wh - wi, written through *wo before the check */
     v3 r = vsub(vscale(wh, 2.f * whdotwi), wi);
@@ -456,6 +459,37 @@ int cvro_ggx_sample(const float alpha[2], float eta, const float wi_in[3],
   return 1;
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* Optional decision / event log of ONE path (cvro_trace_path_logged): used by   */
+/* the GPU parity tests to show that a path whose radiance differs from the      */
+/* oracle's shares its event prefix with it up to one near-tie decision.         */
+/* The log only OBSERVES: no arithmetic of the path loop changes.                */
+/* ------------------------------------------------------------------------- */
+static __thread cvro_trace* g_trace = 0;
+static __thread const cvro_rng* g_trace_rng = 0;
+
+static void log_decision(uint32_t kind, float a, float b) {
+  cvro_trace* t = g_trace;
+  if (!t) return;
+  if (t->n_dec < t->cap_dec) {
+    t->dec_kind[t->n_dec] = kind;
+    t->dec_d[t->n_dec] = g_trace_rng->d;
+    t->dec_a[t->n_dec] = a;
+    t->dec_b[t->n_dec] = b;
+  }
+  t->n_dec++;
+}
+static void log_event(uint32_t code, uint32_t d) {
+  cvro_trace* t = g_trace;
+  if (!t) return;
+  if (t->n_events < t->cap_events) {
+    t->ev_code[t->n_events] = code;
+    t->ev_d[t->n_events] = d;
+  }
+  t->n_events++;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Woodcock tracking (Utilities.cuh:129-155, Medium.h:135-143).  worldToAABB is  */
 /* p - start/range (Q1).  One lookup past max_t is performed (Q10); the accept   */
@@ -469,13 +503,19 @@ static float woodcock(const cvro_scene* sc, v3 o, v3 d, float max_t, cvro_rng* r
   v3 q = vdiv(bmin, extent);
   float event_density = 0.0f;
   float t = 0.0f;
-  do {
+  for (;;) {
     t += -logf(fmaxf(cvro_rng_float(rng), CVRO_EPS)) * inv_max_sigmat;
     v3 p = vsub(vadd(o, vscale(d, t)), q);
     float pp[3] = {p.x, p.y, p.z};
     event_density = sc->scale * cvro_density_lookup(sc, pp);
     ctr->density_lookups++;
-  } while (t <= max_t && event_density * inv_max_sigmat < cvro_rng_float(rng));
+    /* while (t <= max_t && event_density * inv_max_sigmat < u'): u' is drawn only when t <= max_t */
+    log_decision(CVRO_DEC_EXIT, t, max_t);
+    if (!(t <= max_t)) break;
+    float u_accept = cvro_rng_float(rng);
+    log_decision(CVRO_DEC_ACCEPT, event_density * inv_max_sigmat, u_accept);
+    if (!(event_density * inv_max_sigmat < u_accept)) break;
+  }
   return t;
 }
 
@@ -516,6 +556,7 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
       /* Le == 1 (Medium.h:174-177) */
       radiance[0] = thr[0] * 1.f, radiance[1] = thr[1] * 1.f, radiance[2] = thr[2] * 1.f;
       ctr->escaped++;
+      log_event(CVRO_EV_ESCAPE, rng->d);
       return 1;
     }
     int scattered = 0;
@@ -524,6 +565,8 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
       s = woodcock(sc, o, d, dist, rng, ctr);
       scattered = s < dist;
     }
+    const uint32_t ev_d = rng->d; /* draws consumed when the event starts */
+    uint32_t ev_code = scattered ? CVRO_EV_SCATTER : CVRO_EV_BOUNDARY;
     if (!scattered) {
       float fx[3], fy[3], fz[3];
       cvro_frame_from_z(normal, fx, fy, fz);
@@ -548,6 +591,7 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
       /* on the failing reflect/refract checks the LOCAL wo has already been stored
        * into the ray direction (Bsdf.h:25-29 passes &path.ray.d) */
       d = V(wo[0], wo[1], wo[2]);
+      ev_code |= (ok ? CVRO_EVF_OK : 0u) | (wo[2] < 0.f ? CVRO_EVF_WO_NEG : 0u) | (wi[2] < 0.f ? CVRO_EVF_WI_NEG : 0u);
       if (ok) {
         thr[0] *= weight, thr[1] *= weight, thr[2] *= weight;
         d = vadd(vadd(vscale(X, d.x), vscale(Y, d.y)), vscale(Z, d.z));
@@ -573,11 +617,34 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
     }
     /* Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) */
     float p_survive = fminf(1.f, fmaxf(fmaxf(thr[0], thr[1]), thr[2]));
-    if (cvro_rng_float(rng) > p_survive) return 0;
+    float u_rr = cvro_rng_float(rng);
+    log_decision(CVRO_DEC_ROULETTE, u_rr, p_survive);
+    if (u_rr > p_survive) {
+      log_event(ev_code | CVRO_EVF_KILLED, ev_d);
+      return 0;
+    }
+    log_event(ev_code, ev_d);
     thr[0] = thr[0] * 1.f / p_survive;
     thr[1] = thr[1] * 1.f / p_survive;
     thr[2] = thr[2] * 1.f / p_survive;
   }
+}
+
+
+int cvro_trace_path_logged(const cvro_scene* sc, const cvro_camera* cam, int32_t rng_seed,
+                           uint32_t image_id, int variant, uint32_t max_bounces,
+                           float radiance[3], cvro_trace* tr) {
+  cvro_rng rng;
+  cvro_counters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  cvro_rng_init(&rng, rng_seed);
+  tr->n_events = tr->n_dec = 0;
+  tr->d0 = rng.d;
+  g_trace = tr, g_trace_rng = &rng;
+  radiance[0] = radiance[1] = radiance[2] = 0.f;
+  int esc = cvro_trace_path(sc, cam, &rng, image_id, variant, max_bounces, radiance, &ctr);
+  g_trace = 0, g_trace_rng = 0;
+  return esc;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -589,7 +656,9 @@ typedef struct {
   uint64_t begin, end; /* pixel range [begin,end) for image jobs, path range for path jobs */
   uint32_t iterations;
   uint32_t seed;
-  int mode; /* 0 naive image, 1 naive per-path, 2 regen path-rng, 3 regen thread-rng */
+  int mode; /* 0 naive image, 1 naive per-path, 2 regen path-rng, 3 regen thread-rng, 4 seeded per-path */
+  int variant;
+  uint64_t first;
   uint32_t n_persistent;
   uint64_t npix;
   float* out;
@@ -620,6 +689,18 @@ static void* job_main(void* arg) {
           float* px = j->out + 4 * p;
           px[0] += rad[0], px[1] += rad[1], px[2] += rad[2], px[3] = 1.f;
         }
+      }
+    }
+  } else if (j->mode == 4) {
+    /* per-path radiances with Rng(seed + path id): the path set of regenerationSK (rng=xorwow-path),
+     * streamingMK (StreamingVolPTmk_kernel.cuh:55) and of the streaming kernels' per-path form */
+    for (uint64_t path = j->begin; path < j->end; ++path) {
+      cvro_rng rng;
+      cvro_rng_init(&rng, (int32_t)(uint32_t)(j->seed + (uint32_t)path));
+      float* px = j->out + 4 * (path - j->first);
+      px[0] = px[1] = px[2] = px[3] = 0.f;
+      if (cvro_trace_path(j->sc, j->cam, &rng, (uint32_t)(path % j->npix), j->variant, 0, rad, &j->ctr)) {
+        px[0] = rad[0], px[1] = rad[1], px[2] = rad[2], px[3] = 1.f;
       }
     }
   } else if (j->mode == 1) {
@@ -680,6 +761,16 @@ void cvro_trace_paths_naive(const cvro_scene* sc, const cvro_camera* cam,
   job_t j;
   memset(&j, 0, sizeof j);
   j.sc = sc, j.cam = cam, j.mode = 1, j.seed = (uint32_t)first;
+  j.npix = tile_pixels(cam), j.out = out_per_path;
+  run_jobs(&j, count, n_host_threads, ctr, first);
+}
+
+void cvro_trace_paths_seeded(const cvro_scene* sc, const cvro_camera* cam, uint64_t first,
+                             uint64_t count, uint32_t seed, int variant, float* out_per_path,
+                             int n_host_threads, cvro_counters* ctr) {
+  job_t j;
+  memset(&j, 0, sizeof j);
+  j.sc = sc, j.cam = cam, j.mode = 4, j.seed = seed, j.variant = variant, j.first = first;
   j.npix = tile_pixels(cam), j.out = out_per_path;
   run_jobs(&j, count, n_host_threads, ctr, first);
 }

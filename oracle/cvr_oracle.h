@@ -90,6 +90,49 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
                     uint32_t image_id, int variant, uint32_t max_bounces,
                     float radiance[3], cvro_counters* ctr);
 
+/* ---- decision / event log of one path (observes only; see cvr_oracle.c) ----
+ * events: one entry per loop iteration that ended in a scatter or boundary event, plus
+ *   the final escape; ev_d = XORWOW draw counter `d` when the event starts (after the
+ *   Woodcock loop), so two implementations with the same stream agree on (code, d).
+ * decisions: every compare a rounding difference can flip, with the draw counter right
+ *   after the draw involved and the two compared values. */
+enum {
+  CVRO_EV_SCATTER = 1, CVRO_EV_BOUNDARY = 2, CVRO_EV_ESCAPE = 3,
+  CVRO_EVF_OK = 16,      /* boundary: the GGX sample succeeded */
+  CVRO_EVF_WO_NEG = 32,  /* boundary: local wo.z < 0 (reflect / refract side) */
+  CVRO_EVF_WI_NEG = 64,  /* boundary: local wi.z < 0 */
+  CVRO_EVF_KILLED = 128  /* Russian roulette ended the path after this event */
+};
+enum {
+  CVRO_DEC_EXIT = 1,     /* a = t, b = max_t          : continue while t <= max_t  */
+  CVRO_DEC_ACCEPT = 2,   /* a = sigma_t/sigma_max, b = u' : null collision while a < b */
+  CVRO_DEC_ROULETTE = 3, /* a = u, b = p_survive      : killed when a > b          */
+  CVRO_DEC_FRESNEL = 4   /* a = u, b = F              : reflect when a <= b        */
+};
+typedef struct {
+  uint32_t d0; /* draw counter right after Rng(seed) */
+  uint32_t n_events, cap_events;
+  uint32_t* ev_code;
+  uint32_t* ev_d;
+  uint32_t n_dec, cap_dec;
+  uint32_t* dec_kind;
+  uint32_t* dec_d;
+  float* dec_a;
+  float* dec_b;
+} cvro_trace;
+
+/* cvro_trace_path with Rng(rng_seed) and the log filled (counts may exceed the caps:
+ * entries beyond are dropped).  Returns 1 when the path escaped. */
+int cvro_trace_path_logged(const cvro_scene* sc, const cvro_camera* cam, int32_t rng_seed,
+                           uint32_t image_id, int variant, uint32_t max_bounces,
+                           float radiance[3], cvro_trace* tr);
+
+/* Per-path radiances with Rng(seed + path id) and the given variant (pull-back quirk):
+ * out_per_path[4*(p-first)] for p in [first, first+count). */
+void cvro_trace_paths_seeded(const cvro_scene* sc, const cvro_camera* cam, uint64_t first,
+                             uint64_t count, uint32_t seed, int variant, float* out_per_path,
+                             int n_host_threads, cvro_counters* ctr);
+
 /* naiveSK launch: path tid in [0, w*h*iterations), Rng(tid), image_id = tid % (w*h).
  * out = tile accumulation buffer (w*h float4), accumulated into, w set to 1 on
  * every pixel that received an escaped path (Utilities.cuh:15-22).

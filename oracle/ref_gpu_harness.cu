@@ -55,6 +55,13 @@ __constant__ uint c_n_paths;
 
 #include "NaiveVolPTsk_kernel.cuh"
 #include "RegenerationVolPTsk_kernel.cuh"
+// The streamingSK kernel: a syntax-patched COPY of StreamingVolPTsk_kernel.cuh / MortonSort.h that
+// oracle/patch_ref_streaming.py writes into oracle/_ref/patched/ at build time (typename and
+// class-scope-specialisation fixes only); that directory precedes the reference's
+// on the include path for these two files.
+#ifdef CVR_REF_STREAMING
+#include "StreamingVolPTsk_kernel.cuh"
+#endif
 
 #pragma pop_macro("__forceinline__")
 
@@ -80,6 +87,8 @@ struct RefState {
   uint seed = 0;
   uint n_paths = 0;
   uint tile_w = 0, tile_h = 0;
+  Threads d_threads;  // streamingSK queue slice (RenderKernelLauncher.cu:522-538)
+  size_t n_threads = 0;
 };
 static RefState g;
 
@@ -119,6 +128,10 @@ int refgpu_release() {
   if (g.d_density) cudaFreeArray(g.d_density);
   if (g.d_albedo) cudaFreeArray(g.d_albedo);
   if (g.d_out) cudaFree(g.d_out);
+  if (g.n_threads) {
+    cudaFree(g.d_threads.paths.rays.o), cudaFree(g.d_threads.paths.rays.d);
+    cudaFree(g.d_threads.paths.throughputs), cudaFree(g.d_threads.image_ids);
+  }
   g = RefState();
   return 0;
 }
@@ -162,7 +175,9 @@ int refgpu_set_camera(const float inv_view[12], const float raster_to_view[2], u
   return 0;
 }
 
-/* kernel: 0 = NaiveVolPTsk_kernel::d_render, 1 = regeneration single-thread.
+/* kernel: 0 = NaiveVolPTsk_kernel::d_render, 1 = regeneration single-thread,
+ * 2 = StreamingVolPTsk_kernel::d_render as the launcher instantiates it at HEAD (VARIANT
+ * defaulted = kSortingRays, Q16), 3 = the same with VARIANT = kClassic (scan compaction).
  * Renders `iterations` spp of the current tile into a zeroed buffer, copies the raw
  * accumulation (NOT divided) to host_out (tile_w*tile_h float4), reports the kernel
  * time in ms (CUDA events) and the launch shape used.  `seed` is the regeneration
@@ -184,6 +199,48 @@ int refgpu_render(int kernel, unsigned iterations, unsigned seed, float* host_ou
     k<<<grid, block>>>(g.d_out, g.scene);
     CK(cudaEventRecord(e1));
     *grid_out = grid;
+  } else if (kernel == 2 || kernel == 3) {
+#ifdef CVR_REF_STREAMING
+    // StreamingVolPTsk::init / allocateDeviceMemory / launchRender / reset (RenderKernelLauncher.cu:486-575):
+    // block = STREAMING_THREADS_BLOCK, grid = occupancy x SMs (one block per SM when the shared memory
+    // would not fit), queue of grid*block*ITEMS slots, d_paths_head_global = 0, c_seed = seed
+    void* k = kernel == 2
+                  ? (void*)StreamingVolPTsk_kernel::d_render<STREAMING_THREADS_BLOCK, STREAMING_ITEMS_PER_THREAD, RefScene>
+                  : (void*)StreamingVolPTsk_kernel::d_render<STREAMING_THREADS_BLOCK, STREAMING_ITEMS_PER_THREAD, RefScene,
+                                                             StreamingVolPTsk_kernel::kClassic>;
+    block = STREAMING_THREADS_BLOCK;
+    int per_sm = 0, dev = 0;
+    cudaDeviceProp prop;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&prop, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0));
+    int grid = per_sm * prop.multiProcessorCount;
+    if (prop.sharedMemPerMultiprocessor < STREAMING_SHARED_MEMORY * (float)grid / (float)prop.multiProcessorCount)
+      grid = prop.multiProcessorCount;
+    size_t n_threads = (size_t)grid * block * STREAMING_ITEMS_PER_THREAD;
+    if (n_threads != g.n_threads) {
+      if (g.n_threads) {
+        cudaFree(g.d_threads.paths.rays.o), cudaFree(g.d_threads.paths.rays.d);
+        cudaFree(g.d_threads.paths.throughputs), cudaFree(g.d_threads.image_ids);
+      }
+      CK(cudaMalloc(&g.d_threads.paths.rays.o, n_threads * sizeof(float3)));
+      CK(cudaMalloc(&g.d_threads.paths.rays.d, n_threads * sizeof(float3)));
+      CK(cudaMalloc(&g.d_threads.paths.throughputs, n_threads * sizeof(float4)));
+      CK(cudaMalloc(&g.d_threads.image_ids, n_threads * sizeof(uint)));
+      g.n_threads = n_threads;
+    }
+    uint zero = 0;
+    CK(cudaMemcpyToSymbol(StreamingVolPTsk_kernel::d_paths_head_global, &zero, sizeof zero));
+    CK(cudaMemcpyToSymbol(StreamingVolPTsk_kernel::c_seed, &seed, sizeof seed));
+    void* args[] = {&g.d_threads, &g.d_out, &g.scene};
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernel(k, dim3(grid), dim3(block), args, 0, 0));
+    CK(cudaEventRecord(e1));
+    *grid_out = grid;
+#else
+    snprintf(g_err, sizeof g_err, "built without the streamingSK kernel");
+    return 1;
+#endif
   } else {
     auto k = RegenerationVolPTsk_kernel::d_render_single_thread_regeneration<RefScene>;
     CK(cudaOccupancyMaxPotentialBlockSize(&min_grid, &block, k, 0, 0));
@@ -237,6 +294,13 @@ int refgpu_curand_kat(const int* seeds, int n_seeds, int n, unsigned* words, flo
 __global__ void k_hash(const unsigned* in, int n, unsigned* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = utilhash(in[i]);
+}
+int refgpu_has_streaming() {
+#ifdef CVR_REF_STREAMING
+  return 1;
+#else
+  return 0;
+#endif
 }
 int refgpu_utilhash(const unsigned* in, int n, unsigned* out) {
   unsigned *di, *dout;

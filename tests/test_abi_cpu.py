@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.cvr_abi_version() == 2
+    assert lib.cvr_abi_version() == 3
 
 
 def test_no_oracle_in_product_path():

@@ -25,6 +25,43 @@ def _oscene(oracle, sc):
     return oracle.make_scene(sc.density, sc.albedo, sc.box_min, sc.box_max, sc.scale, sc.max_density)
 
 
+def _const_albedo(rgb):
+    a = np.empty((2, 2, 2, 4), np.float32)
+    a[..., :3] = np.asarray(rgb, np.float32)
+    a[..., 3] = 1.0
+    return a
+
+
+def _oracle_sample(cvr, oracle, kl, osc, fov_x, full, tile, off, spp, seed, variant, min_agree):
+    """Bounded-sample ORACLE comparison inside a full-size configuration: the paths of one tile of
+    the full image (same camera, same streams Rng(seed + path id)) traced on the device through
+    the handle's scene as it stands and on the CPU by the oracle; per-path radiances must agree
+    within 1e-4 on at least `min_agree` of the paths (ulp-level flips, tests/test_gpu_parity.py)."""
+    import torch
+
+    iv, rtv = cvr.abi.default_camera(full[0], full[1], fov_x)
+    kl.copyRasterToView(float(rtv[0]), float(rtv[1]))
+    kl.setResolution(tile[0], tile[1])
+    kl.copyPixelIndexRange(float(full[0]), float(full[1]))
+    kl.copyInvViewMatrix(iv)
+    kl.copyOffset(*off)
+    kl.setNIterations(spp)
+    kl.setSampleRange(0, 0)
+    kl.setSeed(seed)
+    n = tile[0] * tile[1] * spp
+    per = torch.zeros((n, 4), dtype=torch.float32, device="cuda:0")
+    kl.tracePaths(0, n, per.data_ptr())
+    kl.sync()
+    got = per.cpu().numpy()
+    cam = oracle.make_camera(tile[0], tile[1], full[0], full[1], off_x=off[0], off_y=off[1], fov_x=fov_x)
+    ref, _ = oracle.trace_paths_seeded(osc, cam, 0, n, seed, variant)
+    same = np.all(np.abs(got[:, :3] - ref[:, :3]) <= 1e-4, axis=1)
+    assert same.mean() >= min_agree, same.mean()
+    assert abs(float(got[:, :3].mean()) - float(ref[:, :3].mean())) <= 0.02 * float(ref[:, :3].mean()) + 2e-3
+    assert int((ref[:, 3] == 1).sum()) > 0
+    return float(same.mean())
+
+
 def test_c1_bucky_full_config_against_cpu_oracle(cvr, oracle):
     sc = cvr.scenes.bucky()
     res, spp = 256, 16
@@ -91,7 +128,7 @@ def test_c2_hetvol_full_size_properties_and_sample(cvr, oracle):
     kl.close()
 
 
-def test_c3_manix_full_size_tiles(cvr):
+def test_c3_manix_full_size_tiles(cvr, oracle):
     sc = cvr.scenes.manix()
     res, spp, tiles = 1024, 256, (10, 10)
     kl = cvr.RegenerationVolPTsk(0)
@@ -114,6 +151,11 @@ def test_c3_manix_full_size_tiles(cvr):
     good = ~np.isnan(a) & ~np.isnan(b)
     assert np.max(np.abs(a[good] - b[good])) <= 2e-5
     assert np.all(img[1020:] == -3.0)
+    # oracle on a bounded sample: tile 45 of the 10 x 10 table (origin 510, 408; 102 x 102) at 2 spp with
+    # the stream base reset() leaves for that tile on one GPU (seed += n_paths per tile)
+    rate = _oracle_sample(cvr, oracle, kl, _oscene(oracle, sc), sc.fov_x, (res, res), (102, 102), (510, 408), 2,
+                          seed=(45 * 102 * 102 * 2) & 0xffffffff, variant=1, min_agree=0.97)
+    print(f"C3 oracle sample: {rate:.4f} of 20808 paths within 1e-4")
     kl.close()
 
 
@@ -259,7 +301,7 @@ def test_vdb_leaves_to_bricks_equals_densified_grid(cvr, tmp_path):
     kb.close()
 
 
-def test_c4_fbm_1024_full_config(cvr):
+def test_c4_fbm_1024_full_config(cvr, oracle):
     """C4: fBm 1024^3 (34.5 GB of lookup cells, generated on the device), albedo 0.99,
     2048 x 2048 x 128 spp = 5.4e8 paths in one launch; spp sharding recomposes at reduced spp."""
     sc = cvr.scenes.fbm_device(1024)
@@ -285,10 +327,20 @@ def test_c4_fbm_1024_full_config(cvr):
         acc += kl.renderImage((512, 512), (1, 1), 8, fov_x=sc.fov_x, sample_first=2 * r, sample_count=2)
     good = ~np.isnan(full[..., :3]) & ~np.isnan(acc[..., :3])
     assert np.max(np.abs(acc[..., :3][good] - full[..., :3][good])) <= 2e-5
+    # oracle on a bounded sample: the SAME 1024^3 voxels generated on the host (4 GiB; the device
+    # generator is pinned to it by test_device_generated_fbm_equals_host_generated), a 48 x 48 tile in
+    # the middle of the 2048^2 image at 2 spp, constant albedo 0.99 as a 2x2x2 volume for the oracle
+    den, _, mx = cvr.abi.synth_volume("fbm", 1024, 1024, 1024, 0, with_albedo=False)
+    assert mx == sc.max_density
+    osc = oracle.make_scene(den, _const_albedo((0.99,) * 3), sc.box_min, sc.box_max, sc.scale, mx)
+    rate = _oracle_sample(cvr, oracle, kl, osc, sc.fov_x, (2048, 2048), (48, 48), (1000, 1000), 2, seed=0, variant=1,
+                          min_agree=0.95)
+    print(f"C4 oracle sample: {rate:.4f} of 4608 paths within 1e-4")
+    del den, osc
     kl.close()
 
 
-def test_c5_sparse_2048_config(cvr):
+def test_c5_sparse_2048_config(cvr, oracle):
     """C5: sparse 2048^3 VDB-style volume in the brick layout (dense cells would be 275 GB),
     4096 x 4096; the full 1024 spp is 1.7e10 paths (the 64-bit path counter is covered by
     test_more_than_2_to_32_paths_in_one_launch), so the image properties are checked at 4 spp:
@@ -326,4 +378,19 @@ def test_c5_sparse_2048_config(cvr):
     assert cl["density_lookups"] < 0.5 * c["density_lookups"]
     assert abs(float(np.nanmean(loc[..., :3])) - float(np.nanmean(full[..., :3]))) <= 0.005
     assert abs(cl["bounces"] - c["bounces"]) / c["bounces"] <= 0.02
+    kl.close()
+    # oracle on a brick-layout scene: the 2048^3 grid does not fit host memory as a dense array (32 GiB),
+    # so the comparison runs on the same generator at 512^3 (512 MiB dense for the oracle, bricks on the
+    # device), a 64 x 64 tile of the 4096^2 image at 2 spp
+    n = 512
+    ssc = cvr.scenes.sparse_fbm(n)
+    kl = cvr.RegenerationVolPTsk(0)
+    kl.setScene(ssc)
+    assert kl.volumeInfo()["layout"] == "brick"
+    den, _, mx = cvr.abi.synth_volume("sparsefbm", n, n, n, 0, with_albedo=False)
+    assert mx == ssc.max_density
+    osc = oracle.make_scene(den, _const_albedo((0.99,) * 3), ssc.box_min, ssc.box_max, ssc.scale, mx)
+    rate = _oracle_sample(cvr, oracle, kl, osc, ssc.fov_x, (res, res), (64, 64), (2000, 2100), 2, seed=0, variant=1,
+                          min_agree=0.95)
+    print(f"C5 oracle sample (sparse 512^3 bricks): {rate:.4f} of 8192 paths within 1e-4")
     kl.close()

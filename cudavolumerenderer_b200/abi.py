@@ -13,6 +13,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CVR_B200_LIB", os.path.join(HERE, "libcvr_b200.so"))  # override: kernel-tuning experiments only
+# experiments only (A/B of two builds in one GPU call): CVR_LIB=<path to another build of the same ABI>
+LIB_PATH = os.environ.get("CVR_LIB", LIB_PATH)
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -77,6 +79,15 @@ class RenderDesc(C.Structure):
     ]
 
 
+class Shard(C.Structure):
+    """cvr_shard: one rank's share of a render (whole tiles + sample range of the tail tiles)."""
+    _fields_ = [("tile_first", C.c_uint32), ("tile_stride", C.c_uint32), ("tile_limit", C.c_uint32),
+                ("tail_first", C.c_uint32), ("tail_limit", C.c_uint32),
+                ("sample_first", C.c_uint32), ("sample_count", C.c_uint32)]
+
+
+SHARD_MODES = {"tiles": 0, "spp": 1, "balanced": 2}
+
 # every symbol include/cvr_abi.h declares: (name, restype, argtypes)
 H = C.c_void_p
 SYMBOLS = [
@@ -110,7 +121,25 @@ SYMBOLS = [
     ("cvr_get_launch_shape", C.c_int, [H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("cvr_resolve_tile", C.c_int, [H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]),
+    ("cvr_resolve_tile_display", C.c_int, [H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                           C.c_uint32, C.c_uint32, C.c_float, C.c_int]),
     ("cvr_render_image", C.c_int, [H, C.POINTER(RenderDesc), C.c_void_p, C.c_void_p]),
+    ("cvr_shard_plan", C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(Shard)]),
+    ("cvr_render_image_sharded", C.c_int, [H, C.POINTER(RenderDesc), C.POINTER(Shard), C.c_void_p, C.c_void_p]),
+    ("cvr_group_create", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(H)]),
+    ("cvr_group_destroy", C.c_int, [H]),
+    ("cvr_group_last_error", C.c_char_p, [H]),
+    ("cvr_group_size", C.c_int, [H, C.POINTER(C.c_int)]),
+    ("cvr_group_member", C.c_int, [H, C.c_int, C.POINTER(H)]),
+    ("cvr_group_set_option", C.c_int, [H, C.c_char_p, C.c_char_p]),
+    ("cvr_group_set_seed", C.c_int, [H, C.c_uint32]),
+    ("cvr_group_set_scene", C.c_int, [H, C.POINTER(SceneDesc)]),
+    ("cvr_group_set_scene_sparse", C.c_int, [H, C.c_void_p]),
+    ("cvr_group_set_scene_procedural", C.c_int, [H, C.c_char_p, C.c_int32, C.c_uint32, C.c_void_p, f32p]),
+    ("cvr_group_render_image", C.c_int, [H, C.POINTER(RenderDesc), C.c_int, C.c_void_p, C.c_void_p]),
+    ("cvr_group_reduce", C.c_int, [H, C.POINTER(C.c_void_p), C.c_uint64]),
+    ("cvr_group_get_counters", C.c_int, [H, C.POINTER(Counters)]),
+    ("cvr_group_reset_counters", C.c_int, [H]),
     ("cvr_tile_table", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p]),
     ("cvr_default_camera", C.c_int, [C.c_uint32, C.c_uint32, C.c_float, f32p, f32p]),
     ("cvr_trace_paths", C.c_int, [H, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -166,6 +195,14 @@ def tile_table(res_x: int, res_y: int, ntx: int, nty: int):
     if rc:
         raise CvrError("cvr_tile_table failed")
     return dim, org
+
+
+def shard_plan(n_tiles: int, iterations: int, rank: int, world: int, mode: str = "balanced") -> Shard:
+    """cvr_shard_plan: rank `rank`'s share of n_tiles tiles x iterations samples (mode tiles | spp | balanced)."""
+    sh = Shard()
+    if mode not in SHARD_MODES or load().cvr_shard_plan(n_tiles, iterations, rank, world, SHARD_MODES[mode], C.byref(sh)):
+        raise ValueError(f"bad shard plan request: tiles {n_tiles} iterations {iterations} rank {rank}/{world} mode {mode}")
+    return sh
 
 
 def default_camera(res_x: int, res_y: int, fov_x: float = 0.7):

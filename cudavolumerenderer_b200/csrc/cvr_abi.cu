@@ -177,6 +177,8 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
     CVR_KS(RNG_XORWOW_PATH, LAYOUT_BRICK)
     CVR_KS(RNG_XORWOW_THREAD, LAYOUT_CELL8)
     CVR_KS(RNG_XORWOW_THREAD, LAYOUT_BRICK)
+    CVR_KS(RNG_PHILOX, LAYOUT_CELL8)
+    CVR_KS(RNG_PHILOX, LAYOUT_BRICK)
 #undef CVR_KS
     return nullptr;
   }
@@ -190,6 +192,8 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
     CVR_KB(RNG_XORWOW_PATH, 1)
     CVR_KB(RNG_XORWOW_THREAD, 0)
     CVR_KB(RNG_XORWOW_THREAD, 1)
+    CVR_KB(RNG_PHILOX, 0)
+    CVR_KB(RNG_PHILOX, 1)
 #undef CVR_KB
     return nullptr;
   }
@@ -201,7 +205,16 @@ kernel_fn pick_warp_kernel(int rng_mode, int layout, int count, int exact, int t
     if (rng_mode == RNG_XORWOW_THREAD)
       return count ? (kernel_fn)k_volpt_warp<RNG_XORWOW_THREAD, LAYOUT_CELL8, true, true, true, W>
                    : (kernel_fn)k_volpt_warp<RNG_XORWOW_THREAD, LAYOUT_CELL8, false, true, true, W>;
+    if (rng_mode == RNG_PHILOX)
+      return count ? (kernel_fn)k_volpt_warp<RNG_PHILOX, LAYOUT_CELL8, true, true, true, W>
+                   : (kernel_fn)k_volpt_warp<RNG_PHILOX, LAYOUT_CELL8, false, true, true, W>;
     return nullptr;
+  }
+  // counter-based stream: fused arithmetic only (its parity is statistical anyway), cell layouts
+  if (rng_mode == RNG_PHILOX) {
+    if (exact || layout != LAYOUT_CELL8) return nullptr;
+    return count ? (kernel_fn)k_volpt_warp<RNG_PHILOX, LAYOUT_CELL8, true, true, false, W>
+                 : (kernel_fn)k_volpt_warp<RNG_PHILOX, LAYOUT_CELL8, false, true, false, W>;
   }
 #define CVR_K(R, L)                                                                                    \
   if (rng_mode == R && layout == L) {                                                                  \
@@ -377,8 +390,7 @@ int effective_pair(cvr_handle h) { return h->pair >= 0 ? h->pair : 1; }
 // The fetch-skip table applies to the fused global-majorant loop of the warp scheduler over a
 // cell layout; "auto" turns it on there.
 bool skip_wanted(cvr_handle h) {
-  if (h->sched != 3 || h->exact || h->tracking || h->scene_layout == LAYOUT_LINEAR || h->rng_mode == RNG_PHILOX)
-    return false;
+  if (h->sched != 3 || h->exact || h->tracking || h->scene_layout == LAYOUT_LINEAR) return false;
   if (!h->d_majorant || !h->maj_dim[0]) return false;
   // auto: on for volumes beyond the L2.  Measured on B200 (1024^2 x 16 spp, Msamples/s off / on):
   // manix 2526 / 2744, fbm 512^3 1079 / 1480, sparse 1024^3 2447 / 2475 -- but bucky 5679 / 5196 and
@@ -400,7 +412,7 @@ int effective_block(cvr_handle h) {
 void plan_skip_table(cvr_handle h, size_t smem_optin) {
   h->skip_bytes = 0;
   if (!skip_wanted(h)) return;
-  const size_t slots = warp_sched_smem_bytes(CVR_WSKIP_BLOCK, effective_wslots(h));
+  const size_t slots = warp_sched_smem_bytes(CVR_WSKIP_BLOCK, effective_wslots(h), 0, warp_slot_bytes(h->rng_mode));
   if (slots + 64 > smem_optin) return;
   const size_t budget = smem_optin - slots;
   for (uint32_t e = 0; e <= 3; ++e) {
@@ -444,13 +456,16 @@ int ensure_init(cvr_handle h) {
   kernel_fn k = pick_kernel(h->sched, h->rng_mode, h->scene_layout, h->counters, h->exact, h->tracking, effective_wslots(h),
                             h->skip_bytes != 0);
   if (!k)
-    return fail(h, "no kernel for sched=%d rng=%d layout=%d exact=%d (philox needs sched=lane; sparse scenes need sched=warp, exact=0)",
-                h->sched, h->rng_mode, h->scene_layout, h->exact);
+    return fail(h, "no kernel for sched=%d rng=%d layout=%d exact=%d tracking=%d (rng=philox needs sched=warp with exact=0 and "
+                "layout=cell8, or sched=lane; sparse scenes need sched=warp, exact=0; tracking=local needs sched=warp|queued)",
+                h->sched, h->rng_mode, h->scene_layout, h->exact, h->tracking);
   cudaFuncAttributes fa;
   CVR_CUDA(h, cudaFuncGetAttributes(&fa, (const void*)k));
   h->regs = fa.numRegs;
   // the warp-private scheduler keeps its path slots in DYNAMIC shared memory (may exceed 48 KB)
-  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(effective_block(h), effective_wslots(h), h->skip_bytes) : 0;
+  h->smem_bytes = h->sched == 3 ? warp_sched_smem_bytes(effective_block(h), effective_wslots(h), h->skip_bytes,
+                                                        warp_slot_bytes(h->rng_mode))
+                                : 0;
   if (h->smem_bytes)
     CVR_CUDA(h, cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   int per_sm = 0;
@@ -731,7 +746,6 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
       h->rng_mode = RNG_PHILOX;
     else
       return fail(h, "rng: unknown value '%s'", value);
-    if (h->rng_mode == RNG_PHILOX) h->sched = 0;  // the wavefront schedulers store XORWOW state only
     if (h->variant == VAR_NAIVE && h->rng_mode == RNG_XORWOW_THREAD)
       return fail(h, "rng=xorwow-thread is not a naiveSK mode (NaiveVolPTsk_kernel.cuh:22 seeds per path)");
     h->inited = false;
@@ -1318,6 +1332,24 @@ int cvr_resolve_tile(cvr_handle h, const void* d_tile, uint32_t tile_w, uint32_t
   return 0;
 }
 
+int cvr_resolve_tile_display(cvr_handle h, const void* d_tile, uint32_t tile_w, uint32_t tile_h, void* d_transfer,
+                             void* d_display, uint32_t full_w, uint32_t full_h, uint32_t off_x, uint32_t off_y, float scale,
+                             int reset_transfer) {
+  CVR_CHECK_HANDLE(h);
+  if (!d_tile || !d_transfer || !d_display) return fail(h, "cvr_resolve_tile_display: null buffer");
+  if (!tile_w || !tile_h || !full_w || !full_h) return fail(h, "cvr_resolve_tile_display: zero size");
+  if (!(scale > 0.f)) return fail(h, "cvr_resolve_tile_display: scale must be positive");
+  if (set_device(h)) return 1;
+  // ImageBufferTransfer.cu:143-147: the transfer buffer starts from zero with the first iteration
+  if (reset_transfer) CVR_CUDA(h, cudaMemsetAsync(d_transfer, 0, (size_t)full_w * full_h * sizeof(float4), h->stream));
+  const uint32_t n = tile_w * tile_h;
+  const int g = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)h->sm_count * 8);
+  k_accumulate_display<<<g, 256, 0, h->stream>>>((const float4*)d_tile, tile_w, tile_h, (float4*)d_transfer, (uchar4*)d_display,
+                                                 full_w, full_h, off_x, off_y, scale);
+  CVR_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 int cvr_tile_table(uint32_t res_x, uint32_t res_y, uint32_t ntx, uint32_t nty, uint32_t tile_dim[2],
                    uint32_t* origins) {
   if (!ntx || !nty || !tile_dim) return 1;
@@ -1348,8 +1380,33 @@ int cvr_default_camera(uint32_t res_x, uint32_t res_y, float fov_x, float inv_vi
   return 0;
 }
 
-int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, void* d_image_out) {
-  CVR_CHECK_HANDLE(h);
+extern "C++" {
+namespace {
+
+// One phase of a render: tiles k = tile_first, tile_first + tile_stride, ... < tile_limit of the
+// reference's tile list, each with sample indices [sample_first, sample_first + sample_count)
+// (count kAllSamples = up to the iteration count; 0 = nothing).  Phases of one call own disjoint tiles.
+constexpr uint32_t kAllSamples = 0xffffffffu;
+struct RenderPhase {
+  uint32_t tile_first, tile_stride, tile_limit, sample_first, sample_count;
+};
+// the phase's sample range against the iteration count: false = nothing to render
+bool phase_samples(cvr_handle h, const RenderPhase& ph, uint32_t iterations) {
+  if (ph.sample_first >= iterations) return false;
+  const uint32_t cnt = ph.sample_count == kAllSamples ? iterations - ph.sample_first : ph.sample_count;
+  if (!cnt) return false;
+  h->sample_first = ph.sample_first, h->sample_count = cnt;
+  return true;
+}
+
+bool phase_owns(const RenderPhase& ph, uint32_t k) {
+  return k >= ph.tile_first && k < ph.tile_limit && (k - ph.tile_first) % ph.tile_stride == 0;
+}
+
+// CudaVolPath::render (CudaVolPath.cpp:338-347) over the given phases.  `zero_image`: clear the
+// resolved image first (multi-GPU: every rank contributes a full-resolution image to a sum).
+int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* phases, int n_phases, float* host_image,
+                  void* d_image_out, bool zero_image, bool sync_at_end) {
   if (!r) return fail(h, "cvr_render_image: null desc");
   if (!r->res_x || !r->res_y || !r->n_tiles_x || !r->n_tiles_y || !r->iterations)
     return fail(h, "cvr_render_image: zero resolution / tiles / iterations");
@@ -1372,8 +1429,6 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
   if (ensure_init(h) || ensure_allocated(h)) return 1;
   cvr_set_iterations(h, r->iterations);
   cvr_set_inv_view_matrix(h, inv_view);
-  cvr_set_sample_range(h, r->sample_first, r->sample_count);
-  if (check_sample_range(h)) return 1;
 
   const size_t image_px = (size_t)r->res_x * r->res_y;
   const size_t tile_px = (size_t)tile_dim[0] * tile_dim[1];
@@ -1384,19 +1439,27 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
     h->d_image_px = image_px;
   }
   float4* d_image = d_image_out ? (float4*)d_image_out : h->d_image;
-  const uint32_t stride = r->tile_stride ? r->tile_stride : 1;
-  const uint32_t first = r->tile_first;
+  if (zero_image) CVR_CUDA(h, cudaMemsetAsync(d_image, 0, image_px * sizeof(float4), h->stream));
   const uint32_t n_paths_tile = (uint32_t)tile_px * r->iterations;  // uint, RenderKernelLauncher.cu:125
   // stream base of global tile k = seed0 + k * step, i.e. what reset() accumulates on one GPU
   const uint32_t seed0 = h->variant == VAR_NAIVE ? 0u : h->seed;
   const uint32_t seed_step = (h->variant == VAR_REGEN || h->variant == VAR_STREAM_MK) ? n_paths_tile : h->variant == VAR_STREAM ? 1u : 0u;
-  unsigned long long pb, pe;
-  path_range(h, pb, pe);
   const float scale = (float)r->iterations;  // UtilityFunctors::Scale(current_iteration_)
   const int rg = (int)std::min<size_t>((tile_px + 255) / 256, (size_t)h->sm_count * 8);
+  auto owned = [&](uint32_t k) {
+    for (int i = 0; i < n_phases; ++i)
+      if (phase_owns(phases[i], k)) return true;
+    return false;
+  };
+  for (int i = 0; i < n_phases; ++i) {
+    if (!phases[i].tile_stride) return fail(h, "cvr_render_image: zero tile stride");
+    for (int j = 0; j < i; ++j)
+      for (uint32_t k = 0; k < n_tiles; ++k)
+        if (phase_owns(phases[i], k) && phase_owns(phases[j], k)) return fail(h, "cvr_render_image: phases share tile %u", k);
+  }
 
   if (r->fuse_tiles) {
-    // one launch over every owned tile, accumulating straight into a full-resolution
+    // one launch per phase over every tile it owns, accumulating straight into a full-resolution
     // buffer; same pixels, same streams as the loop below
     if (h->d_tile_px < image_px) {
       cudaFree(h->d_tile);
@@ -1413,13 +1476,20 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
     CVR_CUDA(h, cudaMemcpyAsync(h->d_origins, origins.data(), n_tiles * sizeof(uint2),
                                 cudaMemcpyHostToDevice, h->stream));
     CVR_CUDA(h, cudaMemsetAsync(h->d_tile, 0, image_px * sizeof(float4), h->stream));
-    uint32_t n_mine = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
-    if (n_mine) {
-      if (launch(h, h->d_tile, r->res_x, 1, h->d_origins, n_mine, first, stride, seed0, seed_step,
-                 nullptr, pb, pe))
+    for (int i = 0; i < n_phases; ++i) {
+      const RenderPhase& ph = phases[i];
+      const uint32_t limit = std::min(ph.tile_limit, n_tiles);
+      const uint32_t n_mine = ph.tile_first < limit ? (limit - ph.tile_first + ph.tile_stride - 1) / ph.tile_stride : 0;
+      if (!n_mine || !phase_samples(h, ph, r->iterations)) continue;
+      if (check_sample_range(h)) return 1;
+      unsigned long long pb, pe;
+      path_range(h, pb, pe);
+      if (pe == pb) continue;
+      if (launch(h, h->d_tile, r->res_x, 1, h->d_origins, n_mine, ph.tile_first, ph.tile_stride, seed0, seed_step, nullptr, pb, pe))
         return 1;
     }
-    for (uint32_t k = first; k < n_tiles; k += stride) {
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+      if (!owned(k)) continue;
       uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
       k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, ox, oy,
                                                 d_image, r->res_x, ox, oy, scale);
@@ -1432,21 +1502,30 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
       CVR_CUDA(h, cudaMalloc(&h->d_tile, tile_px * sizeof(float4)));
       h->d_tile_px = tile_px;
     }
-    for (uint32_t k = first; k < n_tiles; k += stride) {
-      uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
-      // initRenderState / prepareForNextIterations: zeroed tile buffer (CudaVolPath.cpp:188-208)
-      CVR_CUDA(h, cudaMemsetAsync(h->d_tile, 0, tile_px * sizeof(float4), h->stream));
-      cvr_set_offset(h, ox, oy);  // copyOffset (CudaVolPath.cpp:260)
-      if (launch(h, h->d_tile, tile_dim[0], 0, nullptr, 1, 0, 0, seed0 + k * seed_step, 0, nullptr, pb, pe))
-        return 1;
-      k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], tile_dim[0], 0, 0,
-                                                d_image, r->res_x, ox, oy, scale);
-      CVR_CUDA(h, cudaGetLastError());
+    for (int i = 0; i < n_phases; ++i) {
+      const RenderPhase& ph = phases[i];
+      unsigned long long pb = 0, pe = 0;
+      if (phase_samples(h, ph, r->iterations)) {
+        if (check_sample_range(h)) return 1;
+        path_range(h, pb, pe);
+      }
+      for (uint32_t k = ph.tile_first; k < std::min(ph.tile_limit, n_tiles); k += ph.tile_stride) {
+        uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
+        // initRenderState / prepareForNextIterations: zeroed tile buffer (CudaVolPath.cpp:188-208)
+        CVR_CUDA(h, cudaMemsetAsync(h->d_tile, 0, tile_px * sizeof(float4), h->stream));
+        cvr_set_offset(h, ox, oy);  // copyOffset (CudaVolPath.cpp:260)
+        if (pe > pb && launch(h, h->d_tile, tile_dim[0], 0, nullptr, 1, 0, 0, seed0 + k * seed_step, 0, nullptr, pb, pe)) return 1;
+        k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], tile_dim[0], 0, 0,
+                                                  d_image, r->res_x, ox, oy, scale);
+        CVR_CUDA(h, cudaGetLastError());
+      }
     }
   }
+  cvr_set_sample_range(h, 0, 0);
   pt.mark("setup + launches (host side)");
   if (host_image) {
-    for (uint32_t k = first; k < n_tiles; k += stride) {
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+      if (!owned(k)) continue;
       uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
       size_t off = (size_t)oy * r->res_x + ox;
       CVR_CUDA(h, cudaMemcpy2DAsync(host_image + 4 * off, (size_t)r->res_x * sizeof(float4), d_image + off,
@@ -1455,10 +1534,398 @@ int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, 
     }
   }
   pt.mark("D2H enqueue");
-  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (sync_at_end) CVR_CUDA(h, cudaStreamSynchronize(h->stream));
   pt.mark("final sync (kernel + copies)");
   // what the sequence of reset() calls leaves behind after all tiles
   h->seed += n_tiles * seed_step;
+  return 0;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int cvr_render_image(cvr_handle h, const cvr_render_desc* r, float* host_image, void* d_image_out) {
+  CVR_CHECK_HANDLE(h);
+  if (!r) return fail(h, "cvr_render_image: null desc");
+  if (r->sample_first && r->sample_first >= r->iterations)
+    return fail(h, "cvr_render_image: first sample %u is not below the iteration count %u", r->sample_first, r->iterations);
+  if (r->sample_count && (unsigned long long)r->sample_first + r->sample_count > r->iterations)
+    return fail(h, "cvr_render_image: samples [%u, %llu) exceed the iteration count %u", r->sample_first,
+                (unsigned long long)r->sample_first + r->sample_count, r->iterations);
+  const RenderPhase ph{r->tile_first, r->tile_stride ? r->tile_stride : 1u, 0xffffffffu, r->sample_first,
+                       r->sample_count ? r->sample_count : kAllSamples};
+  return render_phases(h, r, &ph, 1, host_image, d_image_out, false, true);
+}
+
+/* Balanced static sharding (100 tiles over 8 ranks = 13 vs 12):
+ *   mode 0 "tiles"     rank r renders tiles k = r (mod world), all samples
+ *   mode 1 "spp"       every rank renders every tile, samples [first, first + count)
+ *   mode 2 "balanced"  the complete rounds of the interleave (tiles < world * floor(n_tiles / world))
+ *                      go by tile, the left-over tiles are split by SAMPLE INDEX over all ranks:
+ *                      every rank gets n_tiles / world tile-equivalents of work, every (tile,
+ *                      sample) pair is rendered exactly once, with the stream it has on one GPU. */
+int cvr_shard_plan(uint32_t n_tiles, uint32_t iterations, int rank, int world, int mode, cvr_shard* out) {
+  if (!out || world < 1 || rank < 0 || rank >= world || !n_tiles || !iterations || mode < 0 || mode > 2) return 1;
+  memset(out, 0, sizeof *out);
+  const uint32_t w = (uint32_t)world, r = (uint32_t)rank;
+  // sample split of `iterations` over the ranks: remainders go to the low ranks
+  const uint32_t base = iterations / w, rem = iterations % w;
+  const uint32_t s_first = r * base + std::min(r, rem), s_count = base + (r < rem ? 1u : 0u);
+  if (mode == 0) {
+    out->tile_first = r, out->tile_stride = w, out->tile_limit = n_tiles;
+    out->tail_first = out->tail_limit = n_tiles;
+  } else if (mode == 1) {
+    out->tile_first = out->tile_limit = 0, out->tile_stride = 1;  // no whole tiles
+    out->tail_first = 0, out->tail_limit = n_tiles;
+    out->sample_first = s_first, out->sample_count = s_count;
+  } else {
+    const uint32_t whole = (n_tiles / w) * w;
+    out->tile_first = r, out->tile_stride = w, out->tile_limit = whole;
+    out->tail_first = whole, out->tail_limit = n_tiles;
+    out->sample_first = s_first, out->sample_count = s_count;
+  }
+  return 0;
+}
+
+int cvr_render_image_sharded(cvr_handle h, const cvr_render_desc* r, const cvr_shard* sh, float* host_image, void* d_image_out) {
+  CVR_CHECK_HANDLE(h);
+  if (!r || !sh) return fail(h, "cvr_render_image_sharded: null argument");
+  RenderPhase ph[2];
+  int n = 0;
+  if (sh->tile_first < sh->tile_limit)
+    ph[n++] = RenderPhase{sh->tile_first, sh->tile_stride ? sh->tile_stride : 1u, sh->tile_limit, 0u, kAllSamples};
+  // a rank whose sample share of the tail is empty (more ranks than samples) renders nothing of it
+  if (sh->tail_first < sh->tail_limit && sh->sample_count)
+    ph[n++] = RenderPhase{sh->tail_first, 1u, sh->tail_limit, sh->sample_first, sh->sample_count};
+  // every rank's image is a term of a sum over ranks: pixels it does not own must be zero
+  return render_phases(h, r, ph, n, host_image, d_image_out, true, true);
+}
+
+// =========================================================================== device groups
+}  // extern "C" (the group implementation needs C++ linkage for its helpers)
+
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library is loaded with dlopen on first use
+
+#include <thread>
+
+struct cvr_group {
+  std::vector<cvr_handle> members;
+  std::vector<int> devices;
+  std::vector<ncclComm_t> comms;     // empty until the first reduce of a group with > 1 device
+  std::vector<float4*> d_images;     // per-member full-resolution resolved image (group-owned)
+  size_t image_px = 0;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_group_create_error;
+
+int gfail(cvr_group_handle g, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (g)
+    g->err = buf;
+  else
+    g_group_create_error = buf;
+  return 1;
+}
+
+// the few NCCL entry points a framebuffer reduce needs, resolved from libnccl.so.2 at run time
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) {
+    api.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+    return api;
+  }
+#define CVR_NCCL_SYM(field, sym)                                                  \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, sym));         \
+  if (!api.field) {                                                               \
+    api.why = std::string("libnccl has no symbol ") + sym;                        \
+    api.lib = nullptr;                                                            \
+    return api;                                                                   \
+  }
+  CVR_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+  CVR_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  CVR_NCCL_SYM(GroupStart, "ncclGroupStart")
+  CVR_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  CVR_NCCL_SYM(Reduce, "ncclReduce")
+  CVR_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef CVR_NCCL_SYM
+  return api;
+}
+
+int group_comms(cvr_group_handle g) {
+  if (!g->comms.empty()) return 0;
+  NcclApi& N = nccl_api();
+  if (!N.lib) return gfail(g, "cvr_group: %s (groups of more than one device need NCCL)", N.why.c_str());
+  g->comms.assign(g->members.size(), nullptr);
+  ncclResult_t rc = N.CommInitAll(g->comms.data(), (int)g->members.size(), g->devices.data());
+  if (rc != ncclSuccess) {
+    g->comms.clear();
+    return gfail(g, "ncclCommInitAll failed: %s", N.GetErrorString(rc));
+  }
+  return 0;
+}
+
+// run f(rank) on one host thread per member; returns the first failing rank + 1 (0 = all fine)
+template <class F>
+int for_each_member(cvr_group_handle g, F f) {
+  const int n = (int)g->members.size();
+  std::vector<int> rc((size_t)n, 0);
+  if (n == 1) {
+    rc[0] = f(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r) th.emplace_back([&, r]() { rc[(size_t)r] = f(r); });
+    for (auto& t : th) t.join();
+  }
+  for (int r = 0; r < n; ++r)
+    if (rc[(size_t)r]) return r + 1;
+  return 0;
+}
+
+int member_failed(cvr_group_handle g, int bad, const char* what) {
+  return gfail(g, "%s: device %d: %s", what, g->devices[(size_t)bad - 1], cvr_last_error(g->members[(size_t)bad - 1]));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cvr_group_last_error(cvr_group_handle g) { return g ? g->err.c_str() : g_group_create_error.c_str(); }
+
+int cvr_group_create(const char* kernel_name, const int* devices, int n_devices, cvr_group_handle* out) {
+  if (!out) return gfail(nullptr, "cvr_group_create: out is null");
+  *out = nullptr;
+  if (n_devices < 1) return gfail(nullptr, "cvr_group_create: need at least one device");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return gfail(nullptr, "cvr_group_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  cvr_group_handle g = new cvr_group();
+  for (int r = 0; r < n_devices; ++r) {
+    const int dev = devices ? devices[r] : r;
+    for (int q : g->devices)
+      if (q == dev) {
+        cvr_group_destroy(g);
+        return gfail(nullptr, "cvr_group_create: device %d listed twice", dev);
+      }
+    cvr_handle h = nullptr;
+    if (cvr_create(kernel_name, dev, &h)) {
+      std::string msg = cvr_last_error(nullptr);
+      cvr_group_destroy(g);
+      return gfail(nullptr, "cvr_group_create: %s", msg.c_str());
+    }
+    g->members.push_back(h);
+    g->devices.push_back(dev);
+    g->d_images.push_back(nullptr);
+  }
+  *out = g;
+  return 0;
+}
+
+int cvr_group_destroy(cvr_group_handle g) {
+  if (!g) return 0;
+  if (!g->comms.empty()) {
+    NcclApi& N = nccl_api();
+    for (ncclComm_t c : g->comms)
+      if (c && N.lib) N.CommDestroy(c);
+  }
+  for (size_t r = 0; r < g->members.size(); ++r) {
+    if (g->d_images[r]) {
+      cudaSetDevice(g->devices[r]);
+      cudaFree(g->d_images[r]);
+    }
+    cvr_destroy(g->members[r]);
+  }
+  delete g;
+  return 0;
+}
+
+int cvr_group_size(cvr_group_handle g, int* n) {
+  if (!g) return gfail(nullptr, "null group");
+  if (n) *n = (int)g->members.size();
+  return 0;
+}
+
+int cvr_group_member(cvr_group_handle g, int rank, cvr_handle* member) {
+  if (!g) return gfail(nullptr, "null group");
+  if (rank < 0 || rank >= (int)g->members.size() || !member) return gfail(g, "cvr_group_member: rank %d of %zu", rank, g->members.size());
+  *member = g->members[(size_t)rank];
+  return 0;
+}
+
+int cvr_group_set_option(cvr_group_handle g, const char* key, const char* value) {
+  if (!g) return gfail(nullptr, "null group");
+  for (size_t r = 0; r < g->members.size(); ++r)
+    if (cvr_set_option(g->members[r], key, value)) return member_failed(g, (int)r + 1, "cvr_group_set_option");
+  return 0;
+}
+
+int cvr_group_set_seed(cvr_group_handle g, uint32_t seed) {
+  if (!g) return gfail(nullptr, "null group");
+  for (cvr_handle h : g->members) cvr_set_seed(h, seed);
+  return 0;
+}
+
+int cvr_group_set_scene(cvr_group_handle g, const cvr_scene_desc* scene) {
+  if (!g) return gfail(nullptr, "null group");
+  if (int bad = for_each_member(g, [&](int r) { return cvr_set_scene(g->members[(size_t)r], scene); }))
+    return member_failed(g, bad, "cvr_group_set_scene");
+  return 0;
+}
+
+int cvr_group_set_scene_sparse(cvr_group_handle g, const cvr_sparse_desc* scene) {
+  if (!g) return gfail(nullptr, "null group");
+  if (int bad = for_each_member(g, [&](int r) { return cvr_set_scene_sparse(g->members[(size_t)r], scene); }))
+    return member_failed(g, bad, "cvr_group_set_scene_sparse");
+  return 0;
+}
+
+int cvr_group_set_scene_procedural(cvr_group_handle g, const char* kind, int32_t n, uint32_t seed, const cvr_scene_desc* medium,
+                                   float* max_density_out) {
+  if (!g) return gfail(nullptr, "null group");
+  std::vector<float> mx(g->members.size(), 0.f);
+  if (int bad = for_each_member(g, [&](int r) {
+        return cvr_set_scene_procedural(g->members[(size_t)r], kind, n, seed, medium, &mx[(size_t)r]);
+      }))
+    return member_failed(g, bad, "cvr_group_set_scene_procedural");
+  if (max_density_out) *max_density_out = mx[0];
+  return 0;
+}
+
+int cvr_group_reduce(cvr_group_handle g, void* const* d_buffers, uint64_t n_floats) {
+  if (!g) return gfail(nullptr, "null group");
+  if (!d_buffers) return gfail(g, "cvr_group_reduce: null buffer list");
+  const int n = (int)g->members.size();
+  if (n > 1) {
+    if (group_comms(g)) return 1;
+    NcclApi& N = nccl_api();
+    ncclResult_t rc = N.GroupStart();
+    for (int r = 0; r < n && rc == ncclSuccess; ++r) {
+      if (!d_buffers[r]) {
+        N.GroupEnd();
+        return gfail(g, "cvr_group_reduce: buffer %d is null", r);
+      }
+      cudaSetDevice(g->devices[(size_t)r]);
+      // in place on the root; recvbuff is only significant there
+      rc = N.Reduce(d_buffers[r], d_buffers[r], (size_t)n_floats, ncclFloat32, ncclSum, 0, g->comms[(size_t)r],
+                    g->members[(size_t)r]->stream);
+    }
+    ncclResult_t rc2 = N.GroupEnd();
+    if (rc != ncclSuccess || rc2 != ncclSuccess)
+      return gfail(g, "ncclReduce failed: %s", N.GetErrorString(rc != ncclSuccess ? rc : rc2));
+  }
+  for (int r = 0; r < n; ++r) {
+    cudaSetDevice(g->devices[(size_t)r]);
+    cudaError_t e = cudaStreamSynchronize(g->members[(size_t)r]->stream);
+    if (e != cudaSuccess) return gfail(g, "cvr_group_reduce: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int shard_mode, float* host_image, void* d_image_rank0_out) {
+  if (!g) return gfail(nullptr, "null group");
+  if (!desc || !desc->res_x || !desc->res_y || !desc->n_tiles_x || !desc->n_tiles_y || !desc->iterations)
+    return gfail(g, "cvr_group_render_image: zero resolution / tiles / iterations");
+  const int n = (int)g->members.size();
+  const uint32_t n_tiles = desc->n_tiles_x * desc->n_tiles_y;
+  std::vector<cvr_shard> plan((size_t)n);
+  for (int r = 0; r < n; ++r)
+    if (cvr_shard_plan(n_tiles, desc->iterations, r, n, shard_mode, &plan[(size_t)r]))
+      return gfail(g, "cvr_group_render_image: bad shard mode %d", shard_mode);
+  const size_t image_px = (size_t)desc->res_x * desc->res_y;
+  if (g->image_px < image_px) {
+    for (int r = 0; r < n; ++r) {
+      cudaSetDevice(g->devices[(size_t)r]);
+      cudaFree(g->d_images[(size_t)r]);
+      g->d_images[(size_t)r] = nullptr;
+      cudaError_t e = cudaMalloc(&g->d_images[(size_t)r], image_px * sizeof(float4));
+      if (e != cudaSuccess) {
+        g->image_px = 0;
+        return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
+      }
+    }
+    g->image_px = image_px;
+  }
+  std::vector<void*> bufs((size_t)n);
+  for (int r = 0; r < n; ++r) bufs[(size_t)r] = g->d_images[(size_t)r];
+  if (d_image_rank0_out) bufs[0] = d_image_rank0_out;
+  // every rank renders its share into its own zeroed full-resolution image (one host thread each)
+  if (int bad = for_each_member(g, [&](int r) {
+        RenderPhase ph[2];
+        int np = 0;
+        const cvr_shard& sh = plan[(size_t)r];
+        if (sh.tile_first < sh.tile_limit)
+          ph[np++] = RenderPhase{sh.tile_first, sh.tile_stride ? sh.tile_stride : 1u, sh.tile_limit, 0u, kAllSamples};
+        if (sh.tail_first < sh.tail_limit && sh.sample_count)
+          ph[np++] = RenderPhase{sh.tail_first, 1u, sh.tail_limit, sh.sample_first, sh.sample_count};
+        // no sync here: the reduce is queued behind the render on the member's stream
+        return render_phases(g->members[(size_t)r], desc, ph, np, nullptr, bufs[(size_t)r], true, false);
+      }))
+    return member_failed(g, bad, "cvr_group_render_image");
+  if (n > 1) {
+    if (cvr_group_reduce(g, bufs.data(), (uint64_t)image_px * 4)) return 1;
+  }
+  if (host_image) {
+    // the covered region (tile_dim * n_tiles; Q6: remainder pixels are never rendered and left untouched)
+    uint32_t tile_dim[2];
+    cvr_tile_table(desc->res_x, desc->res_y, desc->n_tiles_x, desc->n_tiles_y, tile_dim, nullptr);
+    cudaSetDevice(g->devices[0]);
+    cudaError_t e = cudaMemcpy2DAsync(host_image, (size_t)desc->res_x * sizeof(float4), bufs[0], (size_t)desc->res_x * sizeof(float4),
+                                      (size_t)tile_dim[0] * desc->n_tiles_x * sizeof(float4), (size_t)tile_dim[1] * desc->n_tiles_y,
+                                      cudaMemcpyDeviceToHost, g->members[0]->stream);
+    if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: copy to host: %s", cudaGetErrorString(e));
+  }
+  for (int r = 0; r < n; ++r) {
+    cudaSetDevice(g->devices[(size_t)r]);
+    cudaError_t e = cudaStreamSynchronize(g->members[(size_t)r]->stream);
+    if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int cvr_group_get_counters(cvr_group_handle g, cvr_counters* out) {
+  if (!g) return gfail(nullptr, "null group");
+  if (!out) return gfail(g, "cvr_group_get_counters: null");
+  memset(out, 0, sizeof *out);
+  for (size_t r = 0; r < g->members.size(); ++r) {
+    cvr_counters c;
+    if (cvr_get_counters(g->members[r], &c)) return member_failed(g, (int)r + 1, "cvr_group_get_counters");
+    out->paths += c.paths, out->bounces += c.bounces, out->density_lookups += c.density_lookups;
+    out->albedo_lookups += c.albedo_lookups, out->escaped += c.escaped, out->speculative_lookups += c.speculative_lookups;
+    out->launches += c.launches, out->skipped_fetches += c.skipped_fetches;
+    out->kernel_ms = std::max(out->kernel_ms, c.kernel_ms);
+  }
+  return 0;
+}
+
+int cvr_group_reset_counters(cvr_group_handle g) {
+  if (!g) return gfail(nullptr, "null group");
+  for (size_t r = 0; r < g->members.size(); ++r)
+    if (cvr_reset_counters(g->members[r])) return member_failed(g, (int)r + 1, "cvr_group_reset_counters");
   return 0;
 }
 

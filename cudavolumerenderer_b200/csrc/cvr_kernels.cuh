@@ -485,9 +485,11 @@ CVR_DEV V3 hg_sample_fast(V3 dir, float g, float e1, float e2) {
 // final escape: (code, XORWOW draw counter `d` when the event starts), the same record the CPU oracle
 // of the test suite keeps, so that a test can show where a path whose radiance differs from the CPU oracle's
 // left the common event prefix.
-enum : uint32_t { EV_SCATTER = 1, EV_BOUNDARY = 2, EV_ESCAPE = 3, EVF_OK = 16, EVF_WO_NEG = 32, EVF_WI_NEG = 64, EVF_KILLED = 128 };
+enum : uint32_t { EV_SCATTER = 1, EV_BOUNDARY = 2, EV_ESCAPE = 3, EVF_OK = 16, EVF_WO_NEG = 32, EVF_WI_NEG = 64, EVF_KILLED = 128,
+                  EVF_ZERO = 256 /* the throughput is exactly zero after the event (roulette then always ends the path) */ };
 CVR_DEV uint32_t draw_tag(const Xorwow& g) { return g.d; }
 CVR_DEV uint32_t draw_tag(const Philox& g) { return g.c0 * 4u - g.have; }
+CVR_DEV uint32_t draw_tag(const PhiloxCB& g) { return g.ctr * 4u - g.have; }
 CVR_DEV void log_path_event(const KernelParams& P, uint32_t path_lo, uint32_t index, uint32_t code, uint32_t tag) {
   if (index < P.log_cap) P.path_log[(size_t)path_lo * P.log_cap + index] = make_uint2(code, tag);
 }
@@ -697,6 +699,46 @@ CVR_DEV void track_pair_fast(const KernelParams& P, const TrackInv& I, const Gri
   }
 }
 
+// The same pair of Woodcock steps on the counter-based stream (rng=philox): ONE Philox block is the
+// four words of the pair (step 1: flight, accept; step 2: flight, accept).  When step 1 ends the
+// segment the two words of step 2 are simply dropped -- the next consumer takes a fresh block --
+// so there is no generator roll-back, no parked uniform (a path that left the medium goes to
+// S_BOUNDARY and the boundary event draws its own block) and nothing but the block counter to
+// write back.  Statistical parity only (the draw ORDER differs from the reference's).
+template <int LAYOUT, bool COUNT, bool SKIP = false>
+CVR_DEV void track_pair_cb(const KernelParams& P, const TrackInv& I, const GridRay& G, PathRegs<PhiloxCB>& R,
+                           LaneCounters& C, const SkipTab& S = SkipTab()) {
+  uint32_t q1, r1, q2, r2;
+  R.rng.block(q1, r1, q2, r2);
+  const float k = 2.3283064e-10f, h = 2.3283064e-10f / 2.0f;
+  const float u1 = q1 * k + h, w1 = r1 * k + h, u2 = q2 * k + h, w2 = r2 * k + h;
+  const float t1 = fmaf(lg2_fast(fmaxf(u1, CVR_EPS)), I.neg_ln2_inv_sigmat, R.t);
+  const float t2 = fmaf(lg2_fast(fmaxf(u2, CVR_EPS)), I.neg_ln2_inv_sigmat, t1);
+  CellFetch F1, F2;
+  const bool k1 = cell_fetch_skip<LAYOUT, SKIP>(P, I, S, fmaf(t1, G.gdx, G.g0x), fmaf(t1, G.gdy, G.g0y),
+                                                fmaf(t1, G.gdz, G.g0z), r1, F1);
+  const bool k2 = cell_fetch_skip<LAYOUT, SKIP>(P, I, S, fmaf(t2, G.gdx, G.g0x), fmaf(t2, G.gdy, G.g0y),
+                                                fmaf(t2, G.gdz, G.g0z), r2, F2);
+  F1.v[0] = __fmaf_rn(0.0f, F2.v[7], F1.v[0]);  // both loads in flight before the first blend (track_pair_fast)
+  F1.v[4] = __fmaf_rn(0.0f, F2.v[7], F1.v[4]);
+  const float dens1 = trilerp_fast(F1.v, F1.fx, F1.fy, F1.fz);
+  const float dens2 = trilerp_fast(F2.v, F2.fx, F2.fy, F2.fz);
+  const bool in1 = t1 <= R.dist, in2 = t2 <= R.dist;
+  const bool acc1 = !k1 && !(dens1 * I.sig_ratio < w1), acc2 = !k2 && !(dens2 * I.sig_ratio < w2);
+  const bool cont1 = in1 && !acc1;
+  const float td = cont1 ? t2 : t1;
+  const bool ind = in1 & (acc1 | in2), accd = acc1 | (cont1 & acc2);
+  int st = (td < R.dist) ? S_SCATTER : S_BOUNDARY;
+  st = accd ? st : S_TRACK;
+  R.state = ind ? st : S_BOUNDARY;
+  R.t = td;
+  if (COUNT) {
+    C.pairs += 1u;
+    C.cont += cont1 ? 1u : 0u;
+    if (SKIP) C.skip += (k1 ? 1u : 0u) + (k2 ? 1u : 0u);
+  }
+}
+
 // ---- one step of LOCAL-majorant delta tracking ("tracking=local") ----------------------
 // Same unbiased estimator as Woodcock tracking, but the majorant is piecewise constant
 // over bricks of CVR_BRICK^3 lookup cells (the "majorant mip" of the design): inside a
@@ -860,9 +902,10 @@ CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C
   float e1 = R.rng.next();
   float e2 = R.rng.next();
   R.d = FAST ? hg_sample_fast(R.d, P.med.hg_g, e1, e2) : hg_sample(R.d, P.med.hg_g, e1, e2);
+  const uint32_t ev_zero = LOG && fmaxf(fmaxf(R.thr_x, R.thr_y), R.thr_z) == 0.f ? EVF_ZERO : 0u;
   do_roulette<FAST>(P, R, R.rng);
   if (LOG && P.path_log)
-    log_path_event(P, R.path_lo, ev_index, EV_SCATTER | (R.state == S_IDLE && P.rr ? EVF_KILLED : 0u), ev_tag);
+    log_path_event(P, R.path_lo, ev_index, EV_SCATTER | ev_zero | (R.state == S_IDLE && P.rr ? EVF_KILLED : 0u), ev_tag);
 }
 
 // ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
@@ -914,6 +957,7 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
     }
     ev_code |= dir.z < 0.f ? EVF_WI_NEG : 0u;
   }
+  if (LOG && fmaxf(fmaxf(R.thr_x, R.thr_y), R.thr_z) == 0.f) ev_code |= EVF_ZERO;
   do_roulette<FAST>(P, R, rng);
   if (LOG && P.path_log) log_path_event(P, R.path_lo, ev_index, ev_code | (R.state == S_IDLE && P.rr ? EVF_KILLED : 0u), ev_tag);
   // nobody drew (grazing hit with roulette off): give the parked uniform back to the stream
@@ -1094,6 +1138,75 @@ CVR_DEV void slot_store_dynamic(PathSlot& s, float t, uint32_t meta, const Xorwo
   s.q3 = make_uint4(g.v0, g.v1, g.v2, g.v3);
   s.q4 = make_uint4(g.v4, g.d, __float_as_uint(t), meta);
 }
+
+// ---- path-slot storage of the warp-private scheduler, per generator ------------------------
+// XORWOW: the 80-byte array-of-structs slot above (stride 5 x 16 B: consecutive slots fall on
+// different bank groups).  Counter-based stream (rng=philox): 64 bytes per path -- no generator
+// state beyond the stream id and the block counter -- as FOUR arrays of 16-byte vectors per warp
+// (a 64-byte struct would put every slot of a quarter-warp on two bank groups):
+//   q0[W] o.xyz, dist | q1[W] d.xyz, stream lo | q2[W] thr.xyz, out_idx | q3[W] block counter, t, meta, stream hi
+// A tracking batch loads q0, q1, q3 and stores q3: 4 vector accesses per path instead of 6.
+template <class Rng, int W>
+struct WarpSlots;
+template <int W>
+struct WarpSlots<Xorwow, W> {
+  static constexpr size_t kSlotBytes = sizeof(PathSlot);
+  PathSlot* s;
+  CVR_DEV WarpSlots(unsigned char* warp_base, uint32_t) : s(reinterpret_cast<PathSlot*>(warp_base)) {}
+  CVR_DEV void store(unsigned i, const PathRegs<Xorwow>& R) { slot_store(s[i], R); }
+  CVR_DEV void load(unsigned i, PathRegs<Xorwow>& R) { slot_load(s[i], R); }
+  CVR_DEV void load_track(unsigned i, PathRegs<Xorwow>& R) { slot_load_track(s[i], R); }
+  CVR_DEV void store_static(unsigned i, const PathRegs<Xorwow>& R) { slot_store_static(s[i], R); }
+  CVR_DEV void store_dynamic(unsigned i, float t, uint32_t meta, const Xorwow& g) { slot_store_dynamic(s[i], t, meta, g); }
+};
+template <int W>
+struct WarpSlots<PhiloxCB, W> {
+  static constexpr size_t kSlotBytes = 64;
+  float4* q;               // q[k * W + slot]
+  uint32_t path_lo_base;   // stream lo - this = index of the path in a single-tile launch (per-path debug output)
+  CVR_DEV WarpSlots(unsigned char* warp_base, uint32_t base) : q(reinterpret_cast<float4*>(warp_base)), path_lo_base(base) {}
+  CVR_DEV void unpack_dynamic(const float4& e, PathRegs<PhiloxCB>& R) {
+    R.rng.ctr = __float_as_uint(e.x), R.t = e.y, R.rng.s_hi = __float_as_uint(e.w);
+    const uint32_t meta = __float_as_uint(e.z);
+    R.state = (int)(meta & 7u), R.ncode = (int)((meta >> 3) & 7u), R.bounces = meta >> 6;
+    R.rng.have = 0;  // a block never outlives its batch
+  }
+  CVR_DEV void store_static(unsigned i, const PathRegs<PhiloxCB>& R) {
+    q[i] = make_float4(R.o.x, R.o.y, R.o.z, R.dist);
+    q[W + i] = make_float4(R.d.x, R.d.y, R.d.z, __uint_as_float(R.rng.s_lo));
+    q[2 * W + i] = make_float4(R.thr_x, R.thr_y, R.thr_z, __uint_as_float(R.out_idx));
+  }
+  CVR_DEV void store_dynamic(unsigned i, float t, uint32_t meta, const PhiloxCB& g) {
+    q[3 * W + i] = make_float4(__uint_as_float(g.ctr), t, __uint_as_float(meta), __uint_as_float(g.s_hi));
+  }
+  CVR_DEV void store(unsigned i, const PathRegs<PhiloxCB>& R) {
+    store_static(i, R);
+    store_dynamic(i, R.t, (uint32_t)R.state | ((uint32_t)R.ncode << 3) | (R.bounces << 6), R.rng);
+  }
+  CVR_DEV void load_track(unsigned i, PathRegs<PhiloxCB>& R) {
+    const float4 a = q[i], b = q[W + i], e = q[3 * W + i];
+    R.o = v3(a.x, a.y, a.z), R.dist = a.w;
+    R.d = v3(b.x, b.y, b.z), R.rng.s_lo = __float_as_uint(b.w);
+    unpack_dynamic(e, R);
+  }
+  CVR_DEV void load(unsigned i, PathRegs<PhiloxCB>& R) {
+    const float4 a = q[i], b = q[W + i], c = q[2 * W + i], e = q[3 * W + i];
+    R.o = v3(a.x, a.y, a.z), R.dist = a.w;
+    R.d = v3(b.x, b.y, b.z), R.rng.s_lo = __float_as_uint(b.w);
+    R.thr_x = c.x, R.thr_y = c.y, R.thr_z = c.z, R.out_idx = __float_as_uint(c.w);
+    R.path_lo = R.rng.s_lo - path_lo_base;
+    unpack_dynamic(e, R);
+  }
+};
+template <int RNGM>
+struct WarpRngSel {
+  typedef Xorwow type;
+};
+template <>
+struct WarpRngSel<RNG_PHILOX> {
+  typedef PhiloxCB type;
+};
+inline size_t warp_slot_bytes(int rng_mode) { return rng_mode == RNG_PHILOX ? 64 : sizeof(PathSlot); }
 
 CVR_DEV int sort_key(int state) {
   // TRACK 0, SCATTER 1, BOUNDARY / BOUNDARY_P 2, IDLE 3, everything else (DONE) 4: a packed
@@ -1474,8 +1587,8 @@ __global__ void __launch_bounds__(CVR_BLOCK, CVR_MIN_BLOCKS)
 enum : uint32_t { K_TRACK = 0, K_SCATTER = 1, K_BOUNDARY = 2, K_IDLE = 3, K_DONE = 4, K_BUSY = 5 };
 
 // dynamic shared memory of k_volpt_warp for a CTA of `block` threads with W slots per warp
-inline size_t warp_sched_smem_bytes(int block, int W, size_t skip_table_bytes = 0) {
-  return (size_t)(block / 32) * (W * (sizeof(PathSlot) + 1) + 32) + skip_table_bytes;
+inline size_t warp_sched_smem_bytes(int block, int W, size_t skip_table_bytes = 0, size_t slot_bytes = sizeof(PathSlot)) {
+  return (size_t)(block / 32) * (W * (slot_bytes + 1) + 32) + skip_table_bytes;
 }
 
 // (Measured and rejected, twice: in-place refill of finished tracking lanes from waiting
@@ -1499,7 +1612,11 @@ template <int RNGM, int LAYOUT, bool COUNT, bool FAST, bool LOCAL = false, int W
 __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 : CVR_WMIN_BLOCKS)
     k_volpt_warp(const __grid_constant__ KernelParams P) {
   static_assert(!SKIP || (FAST && !LOCAL && LAYOUT != LAYOUT_LINEAR), "the skip table belongs to the fused global-majorant loop");
-  typedef Xorwow Rng;
+  typedef typename WarpRngSel<RNGM>::type Rng;
+  typedef WarpSlots<Rng, W> Slots;
+  constexpr bool CB = RNGM == RNG_PHILOX;  // counter-based stream: 64-byte slots, no roll-back, no parked uniform
+  static_assert(!CB || !LOG, "the event log records XORWOW draw counters");
+  constexpr size_t SB = Slots::kSlotBytes;
   constexpr int K = W / 32;
   static_assert(W % 32 == 0 && K >= 1 && K <= 7, "slots per warp must be 32..224 in steps of 32");
   const unsigned FULL = 0xffffffffu;
@@ -1507,11 +1624,11 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
   const unsigned lane_lt = (1u << lane) - 1u;
 
   extern __shared__ __align__(16) unsigned char s_raw[];
-  PathSlot* const slots = reinterpret_cast<PathSlot*>(s_raw) + warp * W;
-  uint8_t* const keys = s_raw + (size_t)nw * W * sizeof(PathSlot) + warp * W;
-  uint8_t* const list = s_raw + (size_t)nw * W * (sizeof(PathSlot) + 1) + warp * 32;
+  Slots slots(s_raw + (size_t)warp * W * SB, (uint32_t)(P.seed + (uint32_t)P.path_begin));
+  uint8_t* const keys = s_raw + (size_t)nw * W * SB + warp * W;
+  uint8_t* const list = s_raw + (size_t)nw * W * (SB + 1) + warp * 32;
   // SKIP kernels always run with CVR_WSKIP_BLOCK threads: the table offset is a compile-time constant
-  constexpr size_t kTabOffset = (size_t)(CVR_WSKIP_BLOCK / 32) * (W * (sizeof(PathSlot) + 1) + 32);
+  constexpr size_t kTabOffset = (size_t)(CVR_WSKIP_BLOCK / 32) * (W * (SB + 1) + 32);
   SkipTab ST;
   ST.tab = s_raw + kTabOffset;
   if (SKIP) {  // stage the table once per CTA
@@ -1537,8 +1654,11 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     R.ncode = 0;
     R.state = S_IDLE;
     // per-slot stream (thread-rng mode)
-    R.rng.init((int32_t)(P.seed + (blockIdx.x * nw + warp) * W + lane + 32 * j));
-    slot_store(slots[lane + 32 * j], R);
+    if constexpr (CB)
+      R.rng.init(0ull);
+    else
+      R.rng.init((int32_t)(P.seed + (blockIdx.x * nw + warp) * W + lane + 32 * j));
+    slots.store(lane + 32 * j, R);
     st[j] = K_IDLE;
   }
   __syncwarp();
@@ -1589,9 +1709,9 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     if (have) {
       slot = list[lane];
       if (key == 0)
-        slot_load_track(slots[slot], R);
+        slots.load_track(slot, R);
       else
-        slot_load(slots[slot], R);
+        slots.load(slot, R);
     }
 
     // ---------------------------------------------------------------- event of this batch
@@ -1605,7 +1725,7 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     }
     if (have && R.state == S_ISECT) do_isect<COUNT, FAST, LOG>(P, R, C);
     // everything the tracking loop does not touch goes back to the slot now
-    if (key != 0 && have) slot_store_static(slots[slot], R);
+    if (key != 0 && have) slots.store_static(slot, R);
     const uint32_t meta_hi = ((uint32_t)R.ncode << 3) | (R.bounces << 6);
 
     // ---------------------------------------------------------------- Woodcock steps
@@ -1621,7 +1741,16 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
       const GridRay G = grid_ray(I, R.o, R.d);
       // few lanes left and other tracking paths of this warp waiting in slots: stop, they merge
       const int steps = P.track_steps, min_lanes = others_track ? P.track_min_lanes : 0;
-      if (P.pair) {
+      if constexpr (CB) {
+        // counter-based stream: always the pair step, one Philox block per pair (track_pair_cb)
+        int need = 1;
+        for (int it = 0; it < steps; it += 2) {
+          const unsigned trk = __ballot_sync(FULL, R.state == S_TRACK);
+          if (__popc(trk) < need) break;
+          need = max(min_lanes, 1);
+          if (R.state == S_TRACK) track_pair_cb<LAYOUT, COUNT, SKIP>(P, I, G, R, C, ST);
+        }
+      } else if (P.pair) {
         // one test per iteration: stop below `need` tracking lanes; the first iteration runs with any.
         // (Two pairs per vote -- the census is 15 of the ~165 instructions of an iteration and runs
         // with all 32 lanes -- was measured and rejected: the coarser exit costs more than the votes,
@@ -1659,7 +1788,7 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
 
     // ---------------------------------------------------------------- write back + new keys
     if (have) {
-      slot_store_dynamic(slots[slot], R.t, meta_hi | (uint32_t)R.state, R.rng);
+      slots.store_dynamic(slot, R.t, meta_hi | (uint32_t)R.state, R.rng);
       keys[slot] = (uint8_t)sort_key(R.state);
     }
     __syncwarp();
@@ -1789,6 +1918,36 @@ __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w,
     float4 v = tile[(size_t)(y + in_off_y) * in_stride + (x + in_off_x)];
     v.x = v.x / scale, v.y = v.y / scale, v.z = v.z / scale, v.w = v.w / scale;
     image[(size_t)(y + off_y) * full_w + (x + off_x)] = v;
+  }
+}
+
+// ---------------------------------------------------------------- display resolve (progressive / interactive path)
+// DeviceTiledImageBufferTansferDelegate::transfer (ImageBufferTransfer.cu:20-59, 128-157) with
+// ColorPixelTransform<Scale> (:80-100): the tile's accumulation buffer is ADDED into a full-resolution
+// float4 transfer buffer at the tile origin (negative and NaN contributions count as 0, alpha is left
+// alone), and the running sum goes out as 8-bit display pixels: c = clamp(pow(sum / scale, 1 / 2.2) *
+// 255, 0, 255) truncated, alpha 255.  One thread per pixel, rows coalesced (16 B in, 16 B read-modify-
+// write, 4 B out).
+CVR_DEV unsigned char display_channel(float v, float scale) {
+  const float g = __powf(v / scale, 1.f / 2.2f);
+  return (unsigned char)fminf(fmaxf(g * 255.f, 0.f), 255.f);
+}
+__global__ void k_accumulate_display(const float4* __restrict__ tile, uint32_t tile_w, uint32_t tile_h, float4* __restrict__ transfer,
+                                     uchar4* __restrict__ display, uint32_t full_w, uint32_t full_h, uint32_t off_x, uint32_t off_y,
+                                     float scale) {
+  const uint32_t n = tile_w * tile_h;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t x = i % tile_w, y = i / tile_w;
+    const uint32_t ox = x + off_x, oy = y + off_y;
+    if (ox >= full_w || oy >= full_h) continue;  // ImageBufferTransfer.cu:36-38
+    const float4 in = tile[i];
+    const size_t o = (size_t)oy * full_w + ox;
+    float4 t = transfer[o];
+    t.x += in.x > 0 ? in.x : 0;
+    t.y += in.y > 0 ? in.y : 0;
+    t.z += in.z > 0 ? in.z : 0;
+    transfer[o] = t;
+    display[o] = make_uchar4(display_channel(t.x, scale), display_channel(t.y, scale), display_channel(t.z, scale), 255);
   }
 }
 

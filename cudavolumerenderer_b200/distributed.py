@@ -2,12 +2,17 @@
 tiles or by sample index, ONE collective per render (sum of the resolved framebuffers)
 through torch.distributed (NCCL on GPUs; gloo in the CPU tests).  SURVEY.md section 8(e).
 
-Sharding rules (pure functions, tested on CPU):
-  tiles: rank r renders tiles k = r, r+G, ... of the reference's tile list -> disjoint
-         pixels, the image does not depend on G.
-  spp:   rank r renders sample indices [first, first+count) of every pixel; stream ids
-         are seed + sample*npix + pixel, so the multiset of paths equals the 1-GPU run.
+Sharding rules (the library's planner, cvr_shard_plan; pure functions, tested on CPU):
+  tiles:    rank r renders tiles k = r, r+G, ... of the reference's tile list -> disjoint
+            pixels, the image does not depend on G.
+  spp:      rank r renders sample indices [first, first+count) of every pixel; stream ids
+            are seed + sample*npix + pixel, so the multiset of paths equals the 1-GPU run.
+  balanced: the complete rounds of the tile interleave by tile, the n_tiles mod G left-over
+            tiles by sample index: every rank renders n_tiles / G tile-equivalents (100 tiles on
+            8 ranks: 12.5 each instead of 13 / 12).
 Every rank resolves with scale = TOTAL iterations, so the sum over ranks is the image.
+The one-process form of the same thing (N devices, one host thread each, ncclReduce called by
+the library itself) is cudavolumerenderer_b200.DeviceGroup / cvr_group_render_image.
 """
 from __future__ import annotations
 
@@ -31,9 +36,11 @@ def tile_shard(n_tiles: int, rank: int, world: int) -> list[int]:
 
 
 def render_sharded(launcher, res, n_tiles, iterations: int, mode: str, d_image, fov_x: float = 0.7,
-                   inv_view=None, fuse_tiles: bool = True):
+                   inv_view=None, fuse_tiles: bool = True, reduce_to: int | None = None):
     """Render this rank's share into the torch tensor `d_image` (H, W, 4 float32, on the
-    launcher's device; zero-filled here first) and all-reduce it.  Returns d_image."""
+    launcher's device; zero-filled here first) and combine the ranks' images: all-reduce, or
+    -- reduce_to = rank -- a reduce to the one rank that needs the image (half the traffic).
+    Returns d_image (complete on every rank / on rank `reduce_to`)."""
     import torch.distributed as dist
 
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -55,8 +62,17 @@ def render_sharded(launcher, res, n_tiles, iterations: int, mode: str, d_image, 
             launcher.renderImage(res, n_tiles, iterations, sample_first=first, sample_count=count, **kw)
     elif mode == "tiles":
         launcher.renderImage(res, n_tiles, iterations, tile_first=rank, tile_stride=world, **kw)
+    elif mode == "balanced":
+        from . import abi
+
+        sh = abi.shard_plan(n_tiles[0] * n_tiles[1], iterations, rank, world, "balanced")
+        launcher.renderImageSharded(res, n_tiles, iterations, sh, fov_x=fov_x, inv_view=inv_view, fuse_tiles=fuse_tiles,
+                                    d_image=d_image.data_ptr())
     else:
-        raise ValueError("mode must be 'spp' or 'tiles'")
+        raise ValueError("mode must be 'spp', 'tiles' or 'balanced'")
     if world > 1:
-        dist.all_reduce(d_image)
+        if reduce_to is None:
+            dist.all_reduce(d_image)
+        else:
+            dist.reduce(d_image, dst=reduce_to)
     return d_image

@@ -152,6 +152,57 @@ class CudaVolPath : public AbstractProgressiveRenderer {
   }
 };
 
+// Multi-GPU form of CudaVolPath::render: one launcher per device of this process behind the C ABI's
+// device group (cvr_group_*: one host thread per device, the scene replicated, work split by tile
+// and/or sample index, the framebuffers summed into the first device's with ONE ncclReduce).  The
+// image equals the single-GPU render of the same kernel name and seed.
+class GroupVolPath : public AbstractRenderer {
+  cvr_group_handle g_ = nullptr;
+  TilingConfig tiling_config_;
+  uint32_t iterations_;
+  Scene scene_;
+  int shard_mode_;
+
+  void ck(int rc, const char* what) const {
+    if (rc) throw std::runtime_error(std::string(what) + ": " + cvr_group_last_error(g_));
+  }
+
+ public:
+  GroupVolPath(const std::string& kernel, const Scene& scene, TilingConfig tiling, uint32_t iterations, int n_devices,
+               int shard_mode, const LauncherOptions& options = {})
+      : tiling_config_(tiling), iterations_(iterations), scene_(scene), shard_mode_(shard_mode) {
+    if (cvr_group_create(kernel.c_str(), nullptr, n_devices, &g_))
+      throw std::runtime_error(std::string("cvr_group_create: ") + cvr_group_last_error(nullptr));
+    try {
+      for (const auto& kv : options) ck(cvr_group_set_option(g_, kv.first.c_str(), kv.second.c_str()), "setOption");
+      cvr_scene_desc d = scene_.desc();
+      ck(cvr_group_set_scene(g_, &d), "setScene");
+    } catch (...) {
+      cvr_group_destroy(g_);
+      throw;
+    }
+  }
+  ~GroupVolPath() override { cvr_group_destroy(g_); }
+  GroupVolPath(const GroupVolPath&) = delete;
+  GroupVolPath& operator=(const GroupVolPath&) = delete;
+  cvr_group_handle group() const { return g_; }
+
+  void render(Buffer2D out) override {
+    if (out.pitch_bytes != (size_t)tiling_config_.resolution.x * 16)
+      throw std::runtime_error("GroupVolPath::render: the output image must be dense float4 rows");
+    cvr_render_desc r{};
+    r.res_x = tiling_config_.resolution.x, r.res_y = tiling_config_.resolution.y;
+    r.n_tiles_x = tiling_config_.n_tiles.x, r.n_tiles_y = tiling_config_.n_tiles.y;
+    r.iterations = iterations_;
+    r.fov_x = scene_.getCamera()->getFovX();
+    auto rtv = scene_.getCamera()->getRasterToView();
+    r.inv_view = scene_.getCamera()->getInvViewMatrix();
+    r.raster_to_view = rtv.data();
+    r.fuse_tiles = 1;
+    ck(cvr_group_render_image(g_, &r, shard_mode_, (float*)out.data, nullptr), "render");
+  }
+};
+
 // RendererFactory::createRenderer (RendererFactory.h:13-22,37-115): kernel name -> renderer
 inline std::unique_ptr<AbstractProgressiveRenderer> createRenderer(const std::string& kernel, const Scene& scene,
                                                                    TilingConfig tiling, uint32_t iterations,

@@ -32,6 +32,9 @@ struct Options {
   std::vector<unsigned> n_tiles{1, 1}, resolution{1024, 1024};
   bool unified_memory = false;
   int device = 0;
+  int gpus = 1;                  // --gpus N: devices 0..N-1 of this process behind one device group
+  std::string shard = "balanced"; // --shard tiles | spp | balanced
+  bool use_group = false;        // --shard given: go through the device group also with one GPU
   bool dump_scene = false;  // print the loaded scene and exit (no GPU needed)
   std::string dump_raw;     // also write the float4 image as raw little-endian floats
   bool png = false;         // also write <output>.png (Image::savePNG, Image.cpp:35-56)
@@ -50,6 +53,8 @@ void usage() {
                "  --number-of-tiles arg (=1 1)\n"
                "  --use-unified-memory arg (=0)\n"
                "  --device arg (=0)             CUDA device\n"
+               "  --gpus arg (=1)               render on devices 0..N-1 (volume replicated, one NCCL reduce of the framebuffer)\n"
+               "  --shard arg (=balanced)       tiles | spp | balanced: how the work is split over the GPUs\n"
                "  --option key=value            forwarded to cvr_set_option (rng, sched, layout, ...)\n"
                "Scene configuration override:\n"
                "  -i [ --iterations ] arg (=20)\n"
@@ -86,6 +91,10 @@ bool parse(int argc, char** argv, Options& o) {
       o.unified_memory = as_bool(need(i));
     else if (a == "--device")
       o.device = std::stoi(need(i));
+    else if (a == "--gpus")
+      o.gpus = std::stoi(need(i));
+    else if (a == "--shard")
+      o.shard = need(i), o.use_group = true;
     else if (a == "-i" || a == "--iterations")
       o.iterations = (unsigned)std::stoul(need(i));
     else if (a == "-o" || a == "--output")
@@ -204,7 +213,14 @@ int runTest(const Options& o, const Scene& scene) {
     cuda_ck(cudaHostAlloc((void**)&pixels, npx * 16, cudaHostAllocWriteCombined), "cudaHostAlloc");
     std::fill(pixels, pixels + npx * 4, 0.f);
     // --option pairs reach the launcher through the C ABI before init() / setScene()
-    auto renderer = createRenderer(o.kernel, scene, tiling, o.iterations, o.device, o.lib_options);
+    std::unique_ptr<AbstractRenderer> renderer;
+    if (o.gpus > 1 || o.use_group) {
+      const int mode = o.shard == "tiles" ? CVR_SHARD_TILES : o.shard == "spp" ? CVR_SHARD_SPP : o.shard == "balanced" ? CVR_SHARD_BALANCED : -1;
+      if (mode < 0) throw std::runtime_error("--shard expects tiles | spp | balanced");
+      renderer = std::make_unique<GroupVolPath>(o.kernel, scene, tiling, o.iterations, o.gpus, mode, o.lib_options);
+    } else {
+      renderer = createRenderer(o.kernel, scene, tiling, o.iterations, o.device, o.lib_options);
+    }
     auto t1 = std::chrono::steady_clock::now();
     printf("initialization time : %.2f sec \n", std::chrono::duration<float>(t1 - t0).count());
     Buffer2D out = make_buffer2D_float4(pixels, o.resolution[0], o.resolution[1]);

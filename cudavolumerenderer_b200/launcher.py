@@ -281,6 +281,13 @@ class VolPTKernelLauncher:
         self._ck(self._lib.cvr_resolve_tile(self._h, d_tile, tile_w, tile_h, d_image, full_w, full_h,
                                             off_x, off_y, scale), "resolveTile")
 
+    def resolveTileDisplay(self, d_tile: int, tile_w: int, tile_h: int, d_transfer: int, d_display: int, full_w: int,
+                           full_h: int, off_x: int, off_y: int, scale: float, reset_transfer: bool = False) -> None:
+        """DeviceTiledImageBufferTansferDelegate::transfer (ImageBufferTransfer.cu:128-157): accumulate the tile
+        into the float4 transfer buffer and write gamma-corrected uchar4 display pixels."""
+        self._ck(self._lib.cvr_resolve_tile_display(self._h, d_tile, tile_w, tile_h, d_transfer, d_display, full_w, full_h,
+                                                    off_x, off_y, scale, 1 if reset_transfer else 0), "resolveTileDisplay")
+
     def renderImage(self, res, n_tiles=(1, 1), iterations: int = 20, fov_x: float = 0.7, inv_view=None,
                     raster_to_view=None, tile_first: int = 0, tile_stride: int = 1, sample_first: int = 0,
                     sample_count: int = 0, fuse_tiles: bool = False, host_image: np.ndarray | None = None,
@@ -306,6 +313,26 @@ class VolPTKernelLauncher:
             host_image = np.zeros((res[1], res[0], 4), np.float32)
         hp = host_image.ctypes.data if host_image is not None else None
         self._ck(self._lib.cvr_render_image(self._h, C.byref(r), hp, d_image), "renderImage")
+        return host_image
+
+    def renderImageSharded(self, res, n_tiles, iterations: int, shard: "abi.Shard", fov_x: float = 0.7, inv_view=None,
+                           fuse_tiles: bool = True, host_image: np.ndarray | None = None, d_image: int | None = None):
+        """cvr_render_image_sharded: this rank's share (abi.shard_plan) of the image; pixels it does not
+        own are ZERO in the result, which is a term of the sum over ranks."""
+        r = abi.RenderDesc()
+        r.res_x, r.res_y = res
+        r.n_tiles_x, r.n_tiles_y = n_tiles
+        r.iterations, r.fov_x = iterations, fov_x
+        keep = []
+        if inv_view is not None:
+            iv = np.ascontiguousarray(inv_view, np.float32).reshape(12)
+            keep.append(iv)
+            r.inv_view = iv.ctypes.data_as(abi.f32p)
+        r.fuse_tiles = 1 if fuse_tiles else 0
+        if host_image is None and d_image is None:
+            host_image = np.zeros((res[1], res[0], 4), np.float32)
+        hp = host_image.ctypes.data if host_image is not None else None
+        self._ck(self._lib.cvr_render_image_sharded(self._h, C.byref(r), C.byref(shard), hp, d_image), "renderImageSharded")
         return host_image
 
     # -- parity hooks
@@ -371,6 +398,88 @@ class SortingVolPTsk(VolPTKernelLauncher):
 
 KERNELS = {"naiveSK": NaiveVolPTsk, "regenerationSK": RegenerationVolPTsk, "streamingSK": StreamingVolPTsk,
            "streamingMK": StreamingVolPTmk, "sortingSK": SortingVolPTsk}
+
+
+class DeviceGroup:
+    """cvr_group_*: one launcher per device of THIS process (one host thread per device inside the
+    library), every device holding a replica of the scene, the framebuffers combined with one
+    ncclReduce to the first device.  The multi-process form (one process per GPU under torchrun)
+    is cudavolumerenderer_b200.distributed.render_sharded."""
+
+    def __init__(self, kernel: str = "regenerationSK", devices=None, n_devices: int | None = None, **options):
+        self._lib = abi.load()
+        if devices is None:
+            devices = list(range(n_devices or 1))
+        arr = (C.c_int * len(devices))(*devices)
+        g = C.c_void_p()
+        if self._lib.cvr_group_create(kernel.encode(), arr, len(devices), C.byref(g)):
+            raise CvrError("cvr_group_create: " + self._lib.cvr_group_last_error(None).decode())
+        self._g = g
+        self.devices = list(devices)
+        for k, v in options.items():
+            self.setOption(k, v)
+
+    def _ck(self, rc, what):
+        if rc:
+            raise CvrError(f"{what}: {self._lib.cvr_group_last_error(self._g).decode()}")
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.cvr_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setOption(self, key: str, value) -> None:
+        self._ck(self._lib.cvr_group_set_option(self._g, key.encode(), str(value).encode()), f"set_option({key})")
+
+    def setSeed(self, seed: int) -> None:
+        self._ck(self._lib.cvr_group_set_seed(self._g, seed & 0xffffffff), "setSeed")
+
+    def setScene(self, scene) -> None:
+        d = scene.desc()
+        if isinstance(scene, SparseScene):
+            self._ck(self._lib.cvr_group_set_scene_sparse(self._g, C.byref(d)), "setScene(sparse)")
+        elif isinstance(scene, ProceduralScene):
+            mx = C.c_float()
+            self._ck(self._lib.cvr_group_set_scene_procedural(self._g, scene.kind.encode(), scene.n, scene.seed, C.byref(d),
+                                                              C.byref(mx)), "setScene(procedural)")
+            scene.max_density = float(mx.value)
+        else:
+            self._ck(self._lib.cvr_group_set_scene(self._g, C.byref(d)), "setScene")
+        self._scene = scene
+
+    def resolveTileDisplay(self, d_tile: int, tile_w: int, tile_h: int, d_transfer: int, d_display: int, full_w: int,
+                           full_h: int, off_x: int, off_y: int, scale: float, reset_transfer: bool = False) -> None:
+        """DeviceTiledImageBufferTansferDelegate::transfer (ImageBufferTransfer.cu:128-157): accumulate the tile
+        into the float4 transfer buffer and write gamma-corrected uchar4 display pixels."""
+        self._ck(self._lib.cvr_resolve_tile_display(self._h, d_tile, tile_w, tile_h, d_transfer, d_display, full_w, full_h,
+                                                    off_x, off_y, scale, 1 if reset_transfer else 0), "resolveTileDisplay")
+
+    def renderImage(self, res, n_tiles=(1, 1), iterations: int = 20, shard: str = "balanced", fov_x: float = 0.7,
+                    fuse_tiles: bool = True, host_image: np.ndarray | None = None) -> np.ndarray:
+        r = abi.RenderDesc()
+        r.res_x, r.res_y = res
+        r.n_tiles_x, r.n_tiles_y = n_tiles
+        r.iterations, r.fov_x = iterations, fov_x
+        r.fuse_tiles = 1 if fuse_tiles else 0
+        if host_image is None:
+            host_image = np.zeros((res[1], res[0], 4), np.float32)
+        self._ck(self._lib.cvr_group_render_image(self._g, C.byref(r), abi.SHARD_MODES[shard], host_image.ctypes.data, None),
+                 "renderImage")
+        return host_image
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self._lib.cvr_group_get_counters(self._g, C.byref(c)), "counters")
+        return c.as_dict()
+
+    def resetCounters(self) -> None:
+        self._ck(self._lib.cvr_group_reset_counters(self._g), "resetCounters")
 
 
 def createLauncher(kernel: str, device: int = 0, **options) -> VolPTKernelLauncher:

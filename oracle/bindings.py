@@ -63,7 +63,7 @@ class Trace(C.Structure):
 
 
 EV_SCATTER, EV_BOUNDARY, EV_ESCAPE = 1, 2, 3
-EVF_OK, EVF_WO_NEG, EVF_WI_NEG, EVF_KILLED = 16, 32, 64, 128
+EVF_OK, EVF_WO_NEG, EVF_WI_NEG, EVF_KILLED, EVF_ZERO = 16, 32, 64, 128, 256
 DEC_EXIT, DEC_ACCEPT, DEC_ROULETTE, DEC_FRESNEL = 1, 2, 3, 4
 XORWOW_D_STEP = 362437  # the draw counter `d` advances by this per draw
 

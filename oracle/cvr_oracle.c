@@ -617,6 +617,7 @@ int cvro_trace_path(const cvro_scene* sc, const cvro_camera* cam, cvro_rng* rng,
     }
     /* Russian roulette (NaiveVolPTsk_kernel.cuh:75-84) */
     float p_survive = fminf(1.f, fmaxf(fmaxf(thr[0], thr[1]), thr[2]));
+    if (fmaxf(fmaxf(thr[0], thr[1]), thr[2]) == 0.f) ev_code |= CVRO_EVF_ZERO;
     float u_rr = cvro_rng_float(rng);
     log_decision(CVRO_DEC_ROULETTE, u_rr, p_survive);
     if (u_rr > p_survive) {

@@ -101,7 +101,10 @@ enum {
   CVRO_EVF_OK = 16,      /* boundary: the GGX sample succeeded */
   CVRO_EVF_WO_NEG = 32,  /* boundary: local wo.z < 0 (reflect / refract side) */
   CVRO_EVF_WI_NEG = 64,  /* boundary: local wi.z < 0 */
-  CVRO_EVF_KILLED = 128  /* Russian roulette ended the path after this event */
+  CVRO_EVF_KILLED = 128, /* Russian roulette ended the path after this event */
+  CVRO_EVF_ZERO = 256    /* the throughput is exactly zero after the event: GGX_G1 returns 0 when 1 - wo.z^2 <= 0
+                          * (GGX.h:232-236), and wo is not renormalised after refract (GGX.h:45-50), so a
+                          * near-axial refraction is weight 0 or ~1 depending on the last bit of wo.z */
 };
 enum {
   CVRO_DEC_EXIT = 1,     /* a = t, b = max_t          : continue while t <= max_t  */

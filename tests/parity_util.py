@@ -19,7 +19,7 @@ import numpy as np
 D_STEP = 362437
 D_INV = pow(D_STEP, -1, 2 ** 32)
 EV_SCATTER, EV_BOUNDARY, EV_ESCAPE = 1, 2, 3
-EVF_OK, EVF_WO_NEG, EVF_WI_NEG, EVF_KILLED = 16, 32, 64, 128
+EVF_OK, EVF_WO_NEG, EVF_WI_NEG, EVF_KILLED, EVF_ZERO = 16, 32, 64, 128, 256
 DEC_EXIT, DEC_ACCEPT, DEC_ROULETTE, DEC_FRESNEL = 1, 2, 3, 4
 
 
@@ -55,6 +55,10 @@ def explain(dev_events: list[tuple[int, int]], tr: dict, dev_cap: int = 0) -> di
            "accept"      a Woodcock accept test fell the other way; margin = |sigma_t/sigma_max - u'|
            "exit"        the segment-end test t <= max_t fell the other way; margin = |t - max_t| / max_t
            "roulette"    margin = |u - p_survive|
+           "g1-zero"     one side's GGX weight is exactly 0 and the other's is not: GGX_G1 returns 0 when
+                         1 - wo.z^2 <= 0 (GGX.h:232-236) and wo is not renormalised after refract, so a near-axial
+                         refraction sits on a knife edge the last bit of wo.z decides (the reference's own host
+                         and device builds disagree on these paths)
            "fresnel"     reflect / refract choice; margin = |u - F|
            "orientation" the GGX success / side flags differ but not through the Fresnel draw
            "truncated"   a log ran out of capacity before any difference
@@ -78,6 +82,9 @@ def explain(dev_events: list[tuple[int, int]], tr: dict, dev_cap: int = 0) -> di
             out.update(kind="unexplained" if EV_ESCAPE not in (gc & 0xF, oc & 0xF) else "isect", margin=None)
             return out
         diff = gc ^ oc
+        if diff & EVF_ZERO:
+            out.update(kind="g1-zero", margin=None)
+            return out
         if diff & (EVF_OK | EVF_WO_NEG | EVF_WI_NEG):
             k = _first_decision_after(tr, DEC_FRESNEL, od, d0)
             if k is not None and draws(tr["dec_d"][k], d0) <= draws(od, d0) + 3 and not (diff & EVF_WI_NEG):

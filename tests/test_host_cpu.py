@@ -157,13 +157,35 @@ class FakeLauncher:
             acc += ((xs * 31 + ys * 17 + s * 7) % 13) / 13.0
         img[..., 0] += torch.from_numpy(np.where(mine, acc / iterations, 0.0).astype(np.float32))
 
+    def renderImageSharded(self, res, n_tiles, iterations, shard, fov_x=0.7, inv_view=None, fuse_tiles=True,
+                           host_image=None, d_image=None):
+        # the two parts of a cvr_shard: whole tiles with every sample, tail tiles with this rank's samples
+        W, H = res
+        ys, xs = np.mgrid[0:H, 0:W]
+        tw, th = W // n_tiles[0], H // n_tiles[1]
+        tile_id = (ys // th) * n_tiles[0] + (xs // tw)
+        covered = (xs < tw * n_tiles[0]) & (ys < th * n_tiles[1])
+        whole = covered & (tile_id >= shard.tile_first) & (tile_id < shard.tile_limit) & \
+            ((tile_id - shard.tile_first) % max(shard.tile_stride, 1) == 0)
+        tail = covered & (tile_id >= shard.tail_first) & (tile_id < shard.tail_limit)
+        acc = np.zeros((H, W), np.float64)
+        for s in range(iterations):
+            v = ((xs * 31 + ys * 17 + s * 7) % 13) / 13.0
+            in_tail = shard.sample_first <= s < shard.sample_first + shard.sample_count
+            acc += np.where(whole | (tail & in_tail), v, 0.0)
+        IMG[..., 0] += torch.from_numpy((acc / iterations).astype(np.float32))
+
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["CVR_PORT"],
                         rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 out = {}
-for mode in ("spp", "tiles"):
+for mode in ("spp", "tiles", "balanced"):
     IMG = torch.zeros((12, 16, 4), dtype=torch.float32)
     render_sharded(FakeLauncher(), (16, 12), (2, 2), 10, mode, IMG)
     out[mode] = IMG.numpy().copy()
+# 3 x 3 tiles on 2 ranks: 8 whole tiles + 1 tail tile split by sample index, reduced to rank 0 only
+IMG = torch.zeros((12, 18, 4), dtype=torch.float32)
+render_sharded(FakeLauncher(), (18, 12), (3, 3), 7, "balanced", IMG, reduce_to=0)
+out["balanced33"] = IMG.numpy().copy()
 if dist.get_rank() == 0:
     np.savez(os.environ["CVR_OUT"], **out)
 dist.barrier()
@@ -194,9 +216,43 @@ def test_world_size_2_gloo_reduction(tmp_path):
             _, err = p.communicate(timeout=180)
             assert p.returncode == 0, err[-2000:]
         outs[world] = np.load(outp)
-    for mode in ("spp", "tiles"):
+    for mode in ("spp", "tiles", "balanced", "balanced33"):
         assert np.allclose(outs[1][mode], outs[2][mode], atol=1e-6), mode
         assert outs[1][mode][..., 0].sum() > 0
+    assert np.allclose(outs[1]["spp"], outs[1]["balanced"], atol=1e-6)
+
+
+def test_shard_plans_cover_every_tile_sample_pair_once():
+    """cvr_shard_plan (C ABI): over all ranks every (tile, sample) pair is rendered exactly once in
+    every mode, and the balanced mode gives every rank the same amount of work up to one sample of
+    the tail tiles (100 tiles on 8 ranks: 12 whole tiles + 1/8 of 4 tiles each)."""
+    from cudavolumerenderer_b200 import abi
+
+    for n_tiles, iters in ((100, 256), (1, 64), (64, 16), (9, 7), (5, 3), (7, 1)):
+        for world in (1, 2, 3, 4, 8):
+            for mode in ("tiles", "spp", "balanced"):
+                cover = np.zeros((n_tiles, iters), np.int32)
+                work = []
+                for r in range(world):
+                    sh = abi.shard_plan(n_tiles, iters, r, world, mode)
+                    w = 0
+                    for k in range(sh.tile_first, min(sh.tile_limit, n_tiles), max(sh.tile_stride, 1)):
+                        cover[k, :] += 1
+                        w += iters
+                    for k in range(sh.tail_first, sh.tail_limit):
+                        cover[k, sh.sample_first:sh.sample_first + sh.sample_count] += 1
+                        w += sh.sample_count
+                    work.append(w)
+                assert np.all(cover == 1), (n_tiles, iters, world, mode)
+                if mode == "balanced":
+                    assert max(work) - min(work) <= n_tiles % world, (n_tiles, iters, world, work)
+    sh = abi.shard_plan(100, 256, 3, 8, "balanced")
+    assert (sh.tile_first, sh.tile_stride, sh.tile_limit, sh.tail_first, sh.tail_limit, sh.sample_first, sh.sample_count) == \
+        (3, 8, 96, 96, 100, 96, 32)
+    with pytest.raises(ValueError):
+        abi.shard_plan(10, 4, 2, 2, "balanced")
+    with pytest.raises(ValueError):
+        abi.shard_plan(10, 4, 0, 2, "rows")
 
 
 def test_fetch_skip_table_quantisation_is_conservative():

@@ -16,10 +16,17 @@ value      whole-job Msamples/s, scene resident in HBM, device time (CUDA events
 e2e        same metric through the public C-ABI call with HOST buffers: per step the
            volumes are uploaded from pinned host memory (cvr_set_scene), the image is
            rendered (cvr_render_image) and read back into host memory.
-roofline   dominant kernel k_volpt: algorithmic bytes per launch (32 B/density lookup +
-           128 B/albedo lookup + 16 B/path; the counts come from the
-           kernel's own counters) / its mean launch duration (CUDA events recorded by the
-           library around every launch) against MEASURED_PEAKS.json's hbm_gbs.
+roofline   dominant kernel k_volpt_warp.  `achieved` / `frac` keep SURVEY.md 8(d)'s definition --
+           algorithmic bytes per launch (32 B/density lookup + 128 B/albedo lookup + 16 B/path; the
+           counts come from the kernel's own counters) / its mean launch duration (CUDA events
+           recorded by the library around every launch) against MEASURED_PEAKS.json's hbm_gbs --
+           and `bound` says what the launch is really limited by: "l2-gather" when the device
+           layout fits the L2 (then `gather` = L2 -> SM sector traffic against the measured
+           random-sector gather peak at that footprint is the utilisation figure), "hbm" beyond.
+configs    the same measurement for C3 (MANIX 1024^2 x 256 spp, 10x10 tiles: north_star's target)
+           and C4 (fBm 1024^3, 2048^2 x 128 spp: the HBM-resident dense volume), N = 1 only.
+strong_scaling  C3 with the image and spp FIXED, tiles + samples sharded over the N ranks with the
+           balanced plan (cvr_shard_plan) and ONE reduce to rank 0, device-timed, max over ranks.
 cpu_baseline  the reference's OWN regenerationSK kernel (d_render_single_thread_regeneration
            and everything it calls) compiled for the host by g++ from the reference's headers
            (oracle/_ref/libcvr_ref_cpu.so, kind "reference": one persistent CUDA thread per host
@@ -187,7 +194,8 @@ def run_reference(args, rank: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{RES}x{RES} at {spp} spp per step"},
+        "config": {"workload": WORKLOAD, "sample": f"{RES}x{RES} at {spp} spp per step", "spp_scaled": True,
+                   "note": "a rate metric on a bounded sample: the CPU renders 2 of the 64 spp per step"},
         "cpu_baseline": {"value": v, "unit": METRIC, "cores": cores, "kind": kind,
                          "sample": f"{RES}x{RES} at {spp} spp per step, {what}"},
         "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,6 +257,77 @@ def ref_gpu_baseline(sc, spp: int, ours_rgb=None):
         return {"error": str(e)}
 
 
+def traffic_profile(name: str):
+    """ncu-measured hit rates / DRAM traffic of one launch of this workload (profiles/traffic.json, written by hand
+    from the ncu exports named in its "source" fields): they turn the in-run counters into L2 -> SM and DRAM sector
+    traffic.  None when the workload was not profiled."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("workloads", {}).get(name)
+    except Exception:
+        return None
+
+
+def roofline_of(kl, ctr, step_ms, workload: str, const_albedo: bool, footprint_bytes: int, l2_bytes: int):
+    """Roofline object of the launches counted in `ctr` (cvr_counters since the last reset).
+
+    algorithmic bytes = 32 B x density lookups + 128 B x albedo lookups (0 for a constant albedo)
+    + 16 B x paths: layout-independent, what the reference's algorithm asks for.
+    requested bytes = what the kernel's load instructions ask the L1 for: 32 B x cell loads issued (lookups +
+    speculative - skipped) + 96 B x albedo lookups (three 256-bit loads of an rgb cell) + 16 B x paths.
+    L2 -> SM and DRAM sector traffic = requested x the miss rates ncu measured on this workload (profiles/)."""
+    launches = max(int(ctr["launches"]), 1)
+    kern_ms = ctr["kernel_ms"] / launches
+    n_alb = 0 if const_albedo else ctr["albedo_lookups"]
+    alg = (32 * ctr["density_lookups"] + 128 * n_alb + 16 * ctr["paths"]) / launches
+    issued = ctr["density_lookups"] + ctr["speculative_lookups"] - ctr["skipped_fetches"]
+    req = (32 * issued + 96 * n_alb + 16 * ctr["paths"]) / launches
+    peak, peak_src = peaks()
+    achieved = alg / (kern_ms * 1e-3) / 1e9
+    l2_resident = footprint_bytes <= l2_bytes
+    prof = traffic_profile(workload)
+    grid, block, regs = kl.launchShape()
+    r = {"bound": "l2-gather" if l2_resident else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+         "traffic_source": prof.get("source") if prof else None,
+         "what": "achieved = ALGORITHMIC bytes / kernel time (SURVEY.md 8(d)); frac = achieved / measured HBM copy peak -- a "
+                 "throughput figure, not a utilisation: cache reuse among the 8 corners of a cell and L1 / L2 hits put it "
+                 "above the bytes that move.  The utilisation figures are `gather` (L2-resident) and `dram` (HBM-resident).",
+         "kernel": "k_volpt_warp", "peak_source": peak_src, "kernel_ms_per_launch": kern_ms,
+         "algorithmic_bytes_per_launch": alg, "requested_bytes_per_launch": req,
+         "requested_gbs": req / (kern_ms * 1e-3) / 1e9,
+         "cell_loads_issued_fraction": issued / max(ctr["density_lookups"] + ctr["speculative_lookups"], 1),
+         "density_lookups_per_s": ctr["density_lookups"] / (ctr["kernel_ms"] * 1e-3),
+         "kernel_share_of_step": (ctr["kernel_ms"] / step_ms) if step_ms else None,
+         "launch": {"grid": grid, "block": block, "regs": regs},
+         "device_layout_bytes": footprint_bytes, "l2_bytes": l2_bytes}
+    # the measured gather ceilings at this footprint: random 32-byte sectors, 8 independent 256-bit loads in flight per
+    # thread, with the L1 allowed (hashed indices: no reuse) and bypassed (ld.global.nc.L1::no_allocate)
+    fp = min(max(footprint_bytes, 1 << 20), 64 << 30)
+    g_l1 = kl.gatherRoofline(fp, 512, 8)
+    g_nol1 = kl.gatherRoofline(fp, 512, 8, bypass_l1=True)
+    gpeak = max(g_l1, g_nol1)
+    gather = {"what": "random 32-B-sector 256-bit gather microbenchmark at the device layout's footprint (GB/s)",
+              "peak_l1_allowed": g_l1, "peak_l1_bypassed": g_nol1, "peak": gpeak, "unit": "GB/s"}
+    if prof and prof.get("l1_sector_hit_rate") is not None:
+        l2_to_sm = req * (1.0 - prof["l1_sector_hit_rate"])
+        gather.update({"l2_to_sm_gbs": l2_to_sm / (kern_ms * 1e-3) / 1e9, "l1_sector_hit_rate": prof["l1_sector_hit_rate"],
+                       "frac": l2_to_sm / (kern_ms * 1e-3) / 1e9 / gpeak,
+                       "frac_what": "L2 -> SM sector traffic (requested bytes x ncu's L1 sector miss rate) / gather peak"})
+    else:
+        gather.update({"frac": None, "frac_what": "no ncu profile of this workload under profiles/: requested_gbs / peak would count L1 hits"})
+    r["gather"] = gather
+    if prof and prof.get("dram_bytes_per_launch_at") and not l2_resident:
+        # DRAM sector traffic scales with the cell loads issued: bytes per issued load from the profiled launch
+        per_load = prof["dram_bytes_per_launch_at"]["dram_bytes"] / prof["dram_bytes_per_launch_at"]["cell_loads_issued"]
+        dram = per_load * issued / launches
+        r["dram"] = {"dram_gbs": dram / (kern_ms * 1e-3) / 1e9, "dram_bytes_per_cell_load": per_load,
+                     "frac_of_hbm_copy_peak": dram / (kern_ms * 1e-3) / 1e9 / peak,
+                     "frac_of_gather_peak": dram / (kern_ms * 1e-3) / 1e9 / gpeak,
+                     "what": "DRAM bytes per issued cell load from the ncu capture x cell loads issued in this run"}
+    return r
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
     import torch
@@ -272,6 +351,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.init_process_group("nccl", device_id=dev)
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
+            dist.reduce(warm, dst=0)
             torch.cuda.synchronize(dev)
         finally:
             sys.stdout.flush()
@@ -284,6 +364,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     stream = torch.cuda.current_stream(dev)
     kl.setStream(stream.cuda_stream)
     kl.setScene(sc)
+    l2_bytes = int(torch.cuda.get_device_properties(dev).L2_cache_size)
     d_img = torch.zeros((RES, RES, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -294,13 +375,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def step_device():
         flush.fill_(1)  # L2 flush between timed iterations
         kl.setSeed(0)
-        # this rank's 64 sample indices of the 64*N-spp image, then ONE NCCL all-reduce
-        render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x)
+        # this rank's 64 sample indices of the 64*N-spp image, then ONE NCCL reduce to rank 0 (the rank that
+        # keeps the image; an all-reduce would move twice the bytes for nothing)
+        render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x, reduce_to=0)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step_device()
@@ -314,12 +403,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             step_device()
         e1.record(stream)
         barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     ctr = kl.counters()
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     paths_per_step = RES * RES * SPP * world
     value = paths_per_step * args.steps / ms / 1e3
     rgb = d_img[..., :3]
@@ -335,13 +420,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     def step_e2e():
         flush.fill_(1)
-        kl.setScene(sc_pinned)  # H2D of the volumes + device layout build
+        kl.setScene(sc_pinned)  # H2D of the volumes + device layout build (every rank holds a replica)
         kl.setSeed(0)
         if dist is None:
             kl.renderImage((RES, RES), (1, 1), total_spp, fov_x=sc.fov_x, host_image=host_img.numpy())  # D2H inside
         else:
-            render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x)
-            host_img.copy_(d_img, non_blocking=False)
+            render_sharded(kl, (RES, RES), (1, 1), total_spp, "spp", d_img, fov_x=sc.fov_x, reduce_to=0)
+            if rank == 0:  # the image lands on the one rank that keeps it
+                host_img.copy_(d_img, non_blocking=False)
 
     step_e2e()
     barrier()
@@ -356,15 +442,46 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     e1.record(stream)
     barrier()
     wall = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(e0.elapsed_time(e1), wall)  # host-side copies are part of the call: take the wall clock
-    clk.stop()
-    if dist is not None:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall))  # host-side copies are part of the call: take the wall clock
     e2e_value = paths_per_step * n_e2e / ms_e2e / 1e3
     h2d = int(sc.density.nbytes + sc.albedo.nbytes + 12 * 4 + 2 * 4)
     d2h = int(RES * RES * 16)
+
+    # ---- roofline of the dominant kernel (this rank's launches in the timed region)
+    nz, ny, nx = sc.density.shape
+    footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 96)  # density cells + rgb albedo cells
+    roofline = roofline_of(kl, ctr, ms, "hetvol", False, footprint, l2_bytes) if rank == 0 else None
+    main_opts = {k: kl.getOption(k) for k in ("rng", "layout", "sched", "exact", "tracking", "warp_slots", "pair", "skip", "exit_others")}
+    launches = int(ctr["launches"])
+
+    # ---- strong scaling of the tiled configuration (C3: MANIX 1024^2 x 256 spp, 10 x 10 tiles), every N
+    C3_RES, C3_SPP, C3_TILES = 1024, 256, (10, 10)
+    msc = scenes.manix()
+    kl.setScene(msc)
+    d_img3 = torch.zeros((C3_RES, C3_RES, 4), dtype=torch.float32, device=dev)
+
+    def step_c3():
+        flush.fill_(1)
+        kl.setSeed(0)
+        render_sharded(kl, (C3_RES, C3_RES), C3_TILES, C3_SPP, "balanced", d_img3, fov_x=msc.fov_x, reduce_to=0)
+
+    for _ in range(2):
+        step_c3()
+    barrier()
+    kl.resetCounters()
+    n_c3 = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(n_c3):
+        step_c3()
+    e1.record(stream)
+    barrier()
+    ms_c3 = max_over_ranks(e0.elapsed_time(e1)) / n_c3
+    ctr3 = kl.counters()
+    c3_paths = 102 * 102 * 100 * C3_SPP  # Q6: 10 x 10 tiles of 102^2 cover 1020^2 pixels
+    strong = {"workload": "C3 MANIX-like 256x230x256 (procedural stand-in), 1024x1024, 256 spp, 10x10 tiles (1020^2 pixels covered), regenerationSK",
+              "scaling": "strong", "n_gpus": world, "sharding": "balanced (cvr_shard_plan: whole rounds of tiles by rank, left-over tiles by sample index), one reduce to rank 0",
+              "ms_per_step": ms_c3, "value": c3_paths / ms_c3 / 1e3, "unit": METRIC, "steps": n_c3,
+              "image_mean": float(torch.nanmean(d_img3[:1020, :1020, :3]).item()) if rank == 0 else None}
 
     if rank != 0:
         kl.close()
@@ -372,62 +489,74 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (this rank's launches in the timed region)
-    launches = int(ctr["launches"])
-    alg_bytes = 32 * ctr["density_lookups"] + 128 * ctr["albedo_lookups"] + 16 * ctr["paths"]
-    kern_ms = ctr["kernel_ms"] / max(launches, 1)
-    peak, peak_src = peaks()
-    achieved = alg_bytes / max(launches, 1) / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_volpt_dram_bytes_per_launch")
-    except Exception:
-        pass
-    grid, block, regs = kl.launchShape()
-    # measured random-32-B-sector gather peak at this volume's device footprint (L2-resident here)
-    nz, ny, nx = sc.density.shape
-    footprint = (nx + 1) * (ny + 1) * (nz + 1) * (32 + 96)  # density cells + rgb albedo cells
-    gather_peak = kl.gatherRoofline(footprint, 512, 8)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
-                "kernel": {"warp": "k_volpt_warp", "queued": "k_volpt_queued", "sorted": "k_volpt_sorted"}.get(kl.getOption("sched"), "k_volpt"),
-                "peak_source": peak_src,
-                "kernel_ms_per_launch": kern_ms, "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
-                "density_lookups_per_s": ctr["density_lookups"] / (ctr["kernel_ms"] * 1e-3),
-                "kernel_share_of_step": ctr["kernel_ms"] / ms,
-                "launch": {"grid": grid, "block": block, "regs": regs},
-                "gather_roofline": {"what": "random 32-B-sector 256-bit gather microbenchmark at the volume's device footprint",
-                                    "footprint_bytes": footprint, "peak": gather_peak, "unit": "GB/s",
-                                    "frac": achieved / gather_peak}}
-
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    configs = None
     cpu = None
     ref_gpu = None
     if world == 1:
+        # ---- the other single-GPU configurations of BASELINE.json on the same line: C3 (above) and C4
+        mnz, mny, mnx = msc.density.shape
+        fp3 = (mnx + 1) * (mny + 1) * (mnz + 1) * (32 + 96)
+        c3 = {"config": "C3", "workload": strong["workload"], "value": strong["value"], "unit": METRIC, "ms_per_step": ms_c3,
+              "steps": n_c3, "options": {k: kl.getOption(k) for k in ("warp_slots", "skip", "pair")},
+              "lookups_per_path": ctr3["density_lookups"] / max(ctr3["paths"], 1),
+              "roofline": roofline_of(kl, ctr3, ms_c3 * n_c3, "manix", False, fp3, l2_bytes)}
+        del d_img3
+        fsc = scenes.fbm_device(1024)
+        kl.setScene(fsc)
+        C4_RES, C4_SPP = 2048, 128
+        d_img4 = torch.zeros((C4_RES, C4_RES, 4), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            kl.setSeed(0)
+            kl.renderImage((C4_RES, C4_RES), (1, 1), C4_SPP, fov_x=fsc.fov_x, d_image=d_img4.data_ptr())
+        torch.cuda.synchronize(dev)
+        kl.resetCounters()
+        n_c4 = 3
+        e0.record(stream)
+        for _ in range(n_c4):
+            kl.setSeed(0)
+            kl.renderImage((C4_RES, C4_RES), (1, 1), C4_SPP, fov_x=fsc.fov_x, d_image=d_img4.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms_c4 = e0.elapsed_time(e1) / n_c4
+        ctr4 = kl.counters()
+        c4 = {"config": "C4", "workload": "C4 fBm 1024^3 (generated on the device, 34.5 GB of lookup cells), albedo 0.99, 2048x2048, 128 spp, regenerationSK",
+              "value": C4_RES * C4_RES * C4_SPP / ms_c4 / 1e3, "unit": METRIC, "ms_per_step": ms_c4, "steps": n_c4,
+              "options": {k: kl.getOption(k) for k in ("warp_slots", "skip", "pair")},
+              "lookups_per_path": ctr4["density_lookups"] / max(ctr4["paths"], 1),
+              "bounces_per_path": ctr4["bounces"] / max(ctr4["paths"], 1),
+              "image_mean": float(torch.nanmean(d_img4[..., :3]).item()),
+              "roofline": roofline_of(kl, ctr4, ms_c4 * n_c4, "fbm1024", True, kl.volumeInfo()["layout_bytes"], l2_bytes)}
+        del d_img4
+        configs = [c3, c4]
+        kl.setScene(sc)
+        # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu_spp = 16
         v, cores, dt, _, kind, what = cpu_sample(sc, cpu_spp)
         cpu = {"value": v, "unit": METRIC, "cores": cores, "kind": kind,
                "sample": f"{RES}x{RES} at {cpu_spp} spp ({dt:.1f} s), {what}"}
         ref_gpu = ref_gpu_baseline(sc, SPP, rgb.float().cpu().numpy())
+    clk.stop()
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "resolution": [RES, RES], "spp_per_gpu": SPP, "total_spp": total_spp,
-                   "kernel": "regenerationSK", "rng": kl.getOption("rng"), "layout": kl.getOption("layout"),
-                   "sched": kl.getOption("sched"), "arithmetic": "fused (exact=0)" if kl.getOption("exact") == "0" else "reference order (exact=1)",
-                   "tracking": kl.getOption("tracking"), "warp_slots": kl.getOption("warp_slots"),
-                   "speculative_pair_step": kl.getOption("pair"), "fetch_skip_table": kl.getOption("skip"),
-                   "exit_others": kl.getOption("exit_others"),
-                   "sharding": "spp" if world > 1 else "none", "l2": "flushed between steps (256 MiB write)",
+                   "kernel": "regenerationSK", "rng": main_opts["rng"], "layout": main_opts["layout"],
+                   "sched": main_opts["sched"], "arithmetic": "fused (exact=0)" if main_opts["exact"] == "0" else "reference order (exact=1)",
+                   "tracking": main_opts["tracking"], "warp_slots": main_opts["warp_slots"],
+                   "speculative_pair_step": main_opts["pair"], "fetch_skip_table": main_opts["skip"],
+                   "exit_others": main_opts["exit_others"],
+                   "sharding": "spp, one ncclReduce of the framebuffer to rank 0" if world > 1 else "none",
+                   "l2": "flushed between steps (256 MiB write)",
                    "image_mean": img_mean, "nan_pixels": nan_px},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / n_e2e},
         "gpu_launches": launches,
         "roofline": roofline,
+        "configs": configs,
+        "strong_scaling": strong,
         "cpu_baseline": cpu,
         "reference_gpu_kernel": ref_gpu,
         "density_lookups_per_s": roofline["density_lookups_per_s"],

@@ -67,6 +67,7 @@ struct cvr_renderer {
   int tracking = 0;  // 0 = global majorant (reference), 1 = local majorant bricks
   int fix_nan = 0;
   int exit_others = 16;  // KernelParams::exit_others
+  size_t l2_fetch_saved = 0;  // the device's L2 fetch granularity before option "l2_fetch" changed it (0 = untouched)
   int skip = -1;  // fetch-skip table (cvr_kernels.cuh: SkipTab): -1 = auto (on where it applies), 0, 1
 
   // launcher state
@@ -806,6 +807,23 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
   } else if (k == "skip") {
     h->skip = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
     h->inited = false;
+  } else if (k == "l2_fetch") {
+    // cudaLimitMaxL2FetchGranularity (a device-wide HINT): bytes the L2 fetches from DRAM per missing sector.
+    // The lookup gathers ONE 32-byte sector per step at an unpredictable address; ncu on fBm 1024^3 showed
+    // 3.4 DRAM sectors read per sector the kernel asked for at the driver's default.
+    if (set_device(h)) return 1;
+    if (v == "default") {
+      if (h->l2_fetch_saved) CVR_CUDA(h, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, h->l2_fetch_saved));
+    } else {
+      const int g = atoi(value);
+      if (g != 32 && g != 64 && g != 128) return fail(h, "l2_fetch: unknown value '%s' (32 | 64 | 128 | default)", value);
+      if (!h->l2_fetch_saved) {
+        size_t cur = 0;
+        CVR_CUDA(h, cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity));
+        h->l2_fetch_saved = cur ? cur : 64;
+      }
+      CVR_CUDA(h, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
+    }
   } else if (k == "warp_slots") {
     if (v == "auto")
       h->warp_slots = 0;
@@ -867,6 +885,12 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = h->skip_bytes ? std::to_string(1u << h->skip_shift) : std::string(skip_wanted(h) && !h->inited ? "auto" : "0");
   else if (k == "warp_slots")
     v = std::to_string(effective_wslots(h));
+  else if (k == "l2_fetch") {
+    size_t cur = 0;
+    if (set_device(h)) return 1;
+    CVR_CUDA(h, cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity));
+    v = std::to_string(cur);
+  }
   else if (k == "track_steps")
     v = std::to_string(h->track_steps);
   else if (k == "track_min_lanes")
@@ -1994,7 +2018,9 @@ int cvr_gather_roofline(cvr_handle h, uint64_t footprint_bytes, int loads_per_th
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {  // first repetition warms the caches / TLB
     CVR_CUDA(h, cudaEventRecord(e0, h->stream));
-    if (unroll >= 8)
+    if (unroll < 0)  // negative unroll: 8 loads in flight, L1 bypassed (ld.global.nc.L1::no_allocate)
+      k_gather_bench<8, true><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);
+    else if (unroll >= 8)
       k_gather_bench<8><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);
     else if (unroll >= 4)
       k_gather_bench<4><<<grid, block, 0, h->stream>>>(d_cells, (uint32_t)n_cells, loads_per_thread, d_sink);

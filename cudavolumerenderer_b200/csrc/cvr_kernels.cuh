@@ -1956,7 +1956,12 @@ __global__ void k_accumulate_display(const float4* __restrict__ tile, uint32_t t
 // `per_thread` independent 256-bit loads at hashed cell indices of a `n_cells`-cell
 // buffer, UNROLL in flight at a time; the sum defeats dead-code elimination.  This is
 // the measured "gather roofline" denominator for a given footprint (L2-resident or HBM).
-template <int UNROLL>
+CVR_DEV void ldg256_nol1(const float* p, float (&v)[8]) {  // the same load, not allocated in the L1
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+template <int UNROLL, bool NOL1 = false>
 __global__ void __launch_bounds__(256) k_gather_bench(const float* __restrict__ cells, uint32_t n_cells,
                                                        int per_thread, float* sink) {
   uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
@@ -1970,7 +1975,10 @@ __global__ void __launch_bounds__(256) k_gather_bench(const float* __restrict__ 
       h *= 0x2c1b3c6du;
       h ^= h >> 12;
       uint32_t cell = (uint32_t)(((unsigned long long)h * n_cells) >> 32);
-      ldg256(cells + 8 * (size_t)cell, v[u]);
+      if (NOL1)
+        ldg256_nol1(cells + 8 * (size_t)cell, v[u]);
+      else
+        ldg256(cells + 8 * (size_t)cell, v[u]);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) acc += v[u][0] + v[u][7];

@@ -351,9 +351,12 @@ class VolPTKernelLauncher:
                                        w.ctypes.data_as(abi.u32p), u.ctypes.data_as(abi.f32p)), "rngKat")
         return w, u
 
-    def gatherRoofline(self, footprint_bytes: int, loads_per_thread: int = 256, unroll: int = 8) -> float:
-        """Measured random 32-byte-sector gather bandwidth (GB/s) at this footprint."""
+    def gatherRoofline(self, footprint_bytes: int, loads_per_thread: int = 256, unroll: int = 8, bypass_l1: bool = False) -> float:
+        """Measured random 32-byte-sector gather bandwidth (GB/s) at this footprint (bypass_l1: the loads
+        are not allocated in the L1, the pure L2 / HBM -> SM sector rate)."""
         g = C.c_double()
+        if bypass_l1:
+            unroll = -8
         self._ck(self._lib.cvr_gather_roofline(self._h, footprint_bytes, loads_per_thread, unroll, C.byref(g)),
                  "gatherRoofline")
         return g.value

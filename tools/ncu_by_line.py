@@ -1,6 +1,7 @@
 """Join an ncu SASS source page (csv) with nvdisasm line info and aggregate executed
 instructions per source line / per estimator block.
-usage: python tools/ncu_by_line.py <prof.ncu-rep> <lib.so> <mangled-kernel-substring>"""
+usage: python tools/ncu_by_line.py <prof.ncu-rep | exported source page .csv> <lib.so> <mangled-kernel-substring>
+(the .csv form = `ncu -i prof.ncu-rep --page source --csv`, what tools/ncu_export.sh brings back from the GPU box)"""
 import csv, os, re, subprocess, sys, tempfile, collections
 
 rep, so, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
@@ -24,7 +25,10 @@ for ln in dis:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
     if m:
         addr2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+if rep.endswith(".csv"):
+    src = open(rep).read().splitlines()
+else:
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(src))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]

@@ -190,7 +190,7 @@ CVR_DEV float density_at(const MediumParams& m, const TrackInv& I, V3 p) {
   uint32_t kx = min((uint32_t)(x1 + 1), I.nx), ky = min((uint32_t)(y1 + 1), I.ny),
            kz = min((uint32_t)(z1 + 1), I.nz);
   float v[8];
-  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), v);
+  ldg256_d(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), v);
   return trilerp<true>(v[0], v[2], v[4], v[6], v[1], v[3], v[5], v[7], fx, fy, fz);
 }
 
@@ -253,7 +253,7 @@ CVR_DEV void cell_fetch(const MediumParams& m, const TrackInv& I, float cx, floa
   uint32_t kx = min((uint32_t)(__float_as_int(bx) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nx),
            ky = min((uint32_t)(__float_as_int(by) - (CVR_FLOOR_MAGIC_BITS - 1)), I.ny),
            kz = min((uint32_t)(__float_as_int(bz) - (CVR_FLOOR_MAGIC_BITS - 1)), I.nz);
-  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
+  ldg256_d(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
   F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
 }
 // ---- fetch-skip table ----------------------------------------------------------------------
@@ -300,7 +300,7 @@ CVR_DEV bool cell_fetch_skip(const KernelParams& P, const TrackInv& I, const Ski
   // instructions per pair cost more than the wavefronts: manix +5.7 % instead of +8.6 %,
   // fbm 512^3 +31 % instead of +37 % over skip=0.)
   if (SKIP && skip) kx = ky = kz = 0u;
-  ldg256(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
+  ldg256_d<SKIP>(m.dcells + cell_offset<LAYOUT>(m, I, kx, ky, kz), F.v);
   F.fx = cx - (bx - CVR_FLOOR_MAGIC), F.fy = cy - (by - CVR_FLOOR_MAGIC), F.fz = cz - (bz - CVR_FLOOR_MAGIC);
   return skip;
 }

@@ -318,13 +318,20 @@ def roofline_of(kl, ctr, step_ms, workload: str, const_albedo: bool, footprint_b
         gather.update({"frac": None, "frac_what": "no ncu profile of this workload under profiles/: requested_gbs / peak would count L1 hits"})
     r["gather"] = gather
     if prof and prof.get("dram_bytes_per_launch_at") and not l2_resident:
-        # DRAM sector traffic scales with the cell loads issued: bytes per issued load from the profiled launch
-        per_load = prof["dram_bytes_per_launch_at"]["dram_bytes"] / prof["dram_bytes_per_launch_at"]["cell_loads_issued"]
-        dram = per_load * issued / launches
-        r["dram"] = {"dram_gbs": dram / (kern_ms * 1e-3) / 1e9, "dram_bytes_per_cell_load": per_load,
+        # DRAM sector traffic scales with the lookups of the same scene: bytes per density lookup from the profiled launch
+        per_lookup = prof["dram_bytes_per_launch_at"]["dram_bytes"] / prof["dram_bytes_per_launch_at"]["density_lookups"]
+        dram = per_lookup * ctr["density_lookups"] / launches
+        r["traffic"] = dram  # per launch of THIS run, like `achieved`
+        r["traffic_source"] = prof.get("source", "") + " -- DRAM bytes per density lookup of that capture x the lookups counted in this run"
+        r["dram"] = {"dram_gbs": dram / (kern_ms * 1e-3) / 1e9, "dram_bytes_per_density_lookup": per_lookup,
                      "frac_of_hbm_copy_peak": dram / (kern_ms * 1e-3) / 1e9 / peak,
-                     "frac_of_gather_peak": dram / (kern_ms * 1e-3) / 1e9 / gpeak,
-                     "what": "DRAM bytes per issued cell load from the ncu capture x cell loads issued in this run"}
+                     "what": "DRAM read+write bytes per density lookup from the ncu capture x density lookups of this run; the "
+                             "binding resource of an HBM-resident gather is not bytes but L2-missing REQUESTS (44.7 G/s measured, "
+                             "profiles/r2_dram_granule.md): `miss_requests`",
+                     "miss_requests_per_s": issued / launches * (1.0 - prof.get("l1_sector_hit_rate", 0.0)) *
+                                            (1.0 - prof.get("l2_sector_hit_rate", 0.0)) / (kern_ms * 1e-3),
+                     "miss_request_ceiling_per_s": 44.7e9}
+        r["dram"]["frac_of_miss_request_ceiling"] = r["dram"]["miss_requests_per_s"] / r["dram"]["miss_request_ceiling_per_s"]
     return r
 
 

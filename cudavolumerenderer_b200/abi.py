@@ -36,6 +36,13 @@ class SceneDesc(C.Structure):
     ]
 
 
+class SceneFileInfo(C.Structure):  # cvr_scene_file_info_t
+    _fields_ = [
+        ("scene", SceneDesc), ("resolution", C.c_uint32 * 2), ("fov_x", C.c_float), ("inv_view", C.c_float * 12),
+        ("raster_to_view", C.c_float * 2), ("type", C.c_char * 16),
+    ]
+
+
 class Counters(C.Structure):
     _fields_ = [
         ("paths", C.c_uint64), ("bounces", C.c_uint64), ("density_lookups", C.c_uint64),
@@ -151,6 +158,10 @@ SYMBOLS = [
     ("cvr_set_scene_sparse", C.c_int, [C.c_void_p, C.c_void_p]),
     ("cvr_set_scene_procedural", C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_uint32, C.c_void_p, f32p]),
     ("cvr_get_volume_info", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    ("cvr_scene_file_load", C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("cvr_scene_file_info", C.c_int, [C.c_void_p, C.POINTER(SceneFileInfo)]),
+    ("cvr_scene_file_close", C.c_int, [C.c_void_p]),
+    ("cvr_scene_file_last_error", C.c_char_p, []),
     ("cvr_vdb_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     ("cvr_vdb_close", C.c_int, [C.c_void_p]),
     ("cvr_vdb_last_error", C.c_char_p, []),
@@ -210,6 +221,33 @@ def default_camera(res_x: int, res_y: int, fov_x: float = 0.7):
     rtv = np.zeros(2, np.float32)
     load().cvr_default_camera(res_x, res_y, fov_x, iv.ctypes.data_as(f32p), rtv.ctypes.data_as(f32p))
     return iv, rtv
+
+
+def load_scene_file(path: str, scene_type: str = "Auto"):
+    """cvr_scene_file_load + cvr_scene_file_info: the C++ SceneBuilders of the host layer (host/SceneBuilders.h).
+    Returns a dict of numpy COPIES of the volumes and the medium / camera parameters."""
+    lib = load()
+    h = C.c_void_p()
+    if lib.cvr_scene_file_load(path.encode(), scene_type.encode(), C.byref(h)):
+        raise CvrError(lib.cvr_scene_file_last_error().decode())
+    try:
+        info = SceneFileInfo()
+        if lib.cvr_scene_file_info(h, C.byref(info)):
+            raise CvrError(lib.cvr_scene_file_last_error().decode())
+        d = info.scene
+        nx, ny, nz = d.density_dim
+        den = np.ctypeslib.as_array(C.cast(d.density, f32p), shape=(nz, ny, nx)).copy()
+        alb = None
+        if d.albedo:
+            ax, ay, az = d.albedo_dim
+            alb = np.ctypeslib.as_array(C.cast(d.albedo, f32p), shape=(az, ay, ax, 4)).copy()
+        return {"density": den, "albedo": alb, "albedo_const": tuple(d.albedo_const), "box_min": tuple(d.box_min),
+                "box_max": tuple(d.box_max), "scale": float(d.scale), "max_density": float(d.max_density),
+                "hg_g": float(d.hg_g), "ggx_alpha": tuple(d.ggx_alpha), "ggx_eta": float(d.ggx_eta),
+                "resolution": tuple(info.resolution), "fov_x": float(info.fov_x),
+                "inv_view": np.array(info.inv_view, np.float32), "type": info.type.decode()}
+    finally:
+        lib.cvr_scene_file_close(h)
 
 
 def synth_volume(kind: str, nx: int, ny: int, nz: int, seed: int = 0, with_albedo: bool = True):

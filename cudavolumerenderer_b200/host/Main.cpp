@@ -262,27 +262,10 @@ int main(int argc, char** argv) {
     Options o;
     if (!parse(argc, argv, o)) return 0;
     if (o.scene_file.empty()) throw std::runtime_error("Error: no scene file provided");  // ConfigParser.cpp:71-73
-    std::string type = o.scene_type;
-    if (o.scene_file.rfind("synth:", 0) == 0) {
-      type = "Synth";
-    } else if (type == "Auto") {  // ConfigParser.cpp:84-103
-      size_t dot = o.scene_file.find_last_of('.');
-      std::string ext = dot == std::string::npos ? "" : o.scene_file.substr(dot + 1);
-      std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
-      type = ext == "xml" ? "MitsubaXml" : ext == "vdb" ? "Vdb" : "Raw";
-      std::cout << print_prefix << "Auto-detected scene type: " << type << "\n";
-    }
-    std::unique_ptr<SceneBuilder> builder;
-    if (type == "MitsubaXml")
-      builder = std::make_unique<XmlSceneBuilder>(o.scene_file);
-    else if (type == "Vdb")
-      builder = std::make_unique<VDBSceneBuilder>(o.scene_file);
-    else if (type == "Raw")
-      builder = std::make_unique<RawSceneBuilder>(o.scene_file);
-    else if (type == "Synth")
-      builder = std::make_unique<SynthSceneBuilder>(o.scene_file);
-    else
-      throw std::runtime_error("Error: scene type not correct");
+    // ConfigParser.cpp:84-103: "Auto" resolves by extension (makeSceneBuilder, also behind cvr_scene_file_load)
+    std::string type;
+    std::unique_ptr<SceneBuilder> builder = makeSceneBuilder(o.scene_file, o.scene_type, &type);
+    if (o.scene_type == "Auto" && type != "Synth") std::cout << print_prefix << "Auto-detected scene type: " << type << "\n";
     SceneAssembler assembler;
     assembler.setBuilder(std::move(builder));
     Scene scene = assembler.getScene();

@@ -68,7 +68,8 @@ struct HostMedium {
   AABB density_AABB;
   float scale = 1.f;
   float max_density = 1.f;
-  Volume<4> albedo_volume;  // rgb + w
+  Volume<4> albedo_volume;  // rgb + w; empty = the constant albedo below
+  float albedo_const[3] = {1.f, 1.f, 1.f};
   Volume<1> density_volume;
   float hg_g = 0.f;  // Volume.h:20
 };
@@ -91,7 +92,7 @@ class Scene {
     d.albedo = medium_.albedo_volume.data.empty() ? nullptr : medium_.albedo_volume.data.data();
     d.albedo_dim[0] = (int32_t)medium_.albedo_volume.nx, d.albedo_dim[1] = (int32_t)medium_.albedo_volume.ny;
     d.albedo_dim[2] = (int32_t)medium_.albedo_volume.nz;
-    d.albedo_const[0] = d.albedo_const[1] = d.albedo_const[2] = 1.f;
+    for (int c = 0; c < 3; ++c) d.albedo_const[c] = medium_.albedo_const[c];
     d.box_min[0] = medium_.density_AABB.box_min.x, d.box_min[1] = medium_.density_AABB.box_min.y;
     d.box_min[2] = medium_.density_AABB.box_min.z;
     d.box_max[0] = medium_.density_AABB.box_max.x, d.box_max[1] = medium_.density_AABB.box_max.y;

@@ -239,34 +239,60 @@ class VDBSceneBuilder : public SceneBuilder {
   HostMedium getMedium() override { return medium_; }
 };
 
-// procedural stand-ins for the LFS-stub payloads: "synth:bucky|hetvol|manix|fbm[:n]"
+// procedural stand-ins for the LFS-stub payloads:
+//   "synth:<name>[:<n> | :<nx>x<ny>x<nz>][:seed=<s>]"   name = bucky | hetvol | manix | fbm
+// (grid shapes and medium parameters as the reference's loaders would produce them, SURVEY.md 8(d):
+// bucky RawSceneBuilder.h:35-83, hetvol XmlSceneBuilder.h:39-152 with the albedo grid's box (Q3),
+// manix VDBSceneBuilder.h:40-80, fbm = C4's dense noise volume with the constant albedo 0.99)
 class SynthSceneBuilder : public SceneBuilder {
   std::shared_ptr<Camera> camera_;
   HostMedium medium_;
 
  public:
   explicit SynthSceneBuilder(const std::string& spec) {
-    std::string name = spec.substr(spec.find(':') + 1);
-    uint32_t n = 0;
-    if (size_t c = name.find(':'); c != std::string::npos) {
-      n = (uint32_t)std::stoul(name.substr(c + 1));
-      name = name.substr(0, c);
+    std::vector<std::string> part;
+    {
+      std::stringstream ss(spec.substr(spec.find(':') + 1));
+      for (std::string t; std::getline(ss, t, ':');) part.push_back(t);
     }
-    uint32_t nx, ny, nz;
+    if (part.empty()) throw std::invalid_argument("empty synthetic scene name");
+    const std::string name = part[0];
+    uint32_t nx = 0, ny = 0, nz = 0, seed = 0;
+    for (size_t i = 1; i < part.size(); ++i) {
+      const std::string& t = part[i];
+      try {
+        if (t.rfind("seed=", 0) == 0) {
+          seed = (uint32_t)std::stoul(t.substr(5));
+        } else if (size_t x = t.find('x'); x != std::string::npos) {
+          size_t x2 = t.find('x', x + 1);
+          if (x2 == std::string::npos) throw std::invalid_argument(t);
+          nx = (uint32_t)std::stoul(t.substr(0, x)), ny = (uint32_t)std::stoul(t.substr(x + 1, x2 - x - 1));
+          nz = (uint32_t)std::stoul(t.substr(x2 + 1));
+        } else {
+          nx = ny = nz = (uint32_t)std::stoul(t);
+        }
+      } catch (const std::exception&) {
+        throw std::invalid_argument("synthetic scene '" + spec + "': cannot parse '" + t + "' (n | nxXnyXnz | seed=s)");
+      }
+    }
     float fov = 0.7f;
     bool want_albedo = true;
+    medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
     if (name == "bucky") {
-      nx = ny = nz = 32, medium_.scale = 40;
-      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+      if (!nx) nx = ny = nz = 32;
+      medium_.scale = 40;
     } else if (name == "hetvol") {
-      nx = ny = 128, nz = 50, medium_.scale = 800, fov = 0.33f;
+      if (!nx) nx = ny = 128, nz = 50;
+      medium_.scale = 800, fov = 0.33f;
       medium_.density_AABB = {{-0.64f, -0.64f, -0.25f}, {0.64f, 0.64f, 0.25f}};
     } else if (name == "manix") {
-      nx = 256, ny = 230, nz = 256, medium_.scale = 100;
-      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+      if (!nx) nx = 256, ny = 230, nz = 256;
+      medium_.scale = 100;
     } else if (name == "fbm") {
-      nx = ny = nz = n ? n : 256, medium_.scale = 100;
-      medium_.density_AABB = {{-0.5f, -0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}};
+      if (!nx) nx = ny = nz = 256;
+      medium_.scale = 100;
+      want_albedo = false;
+      medium_.albedo_const[0] = medium_.albedo_const[1] = medium_.albedo_const[2] = 0.99f;
     } else {
       throw std::invalid_argument("unknown synthetic scene '" + name + "'");
     }
@@ -278,7 +304,7 @@ class SynthSceneBuilder : public SceneBuilder {
       av.nx = nx, av.ny = ny, av.nz = nz;
       av.data.resize(av.voxels() * 4);
     }
-    if (cvr_synth_volume(name.c_str(), (int32_t)nx, (int32_t)ny, (int32_t)nz, 0, dv.data.data(),
+    if (cvr_synth_volume(name.c_str(), (int32_t)nx, (int32_t)ny, (int32_t)nz, seed, dv.data.data(),
                          want_albedo ? av.data.data() : nullptr, &medium_.max_density))
       throw std::runtime_error("cvr_synth_volume failed for '" + name + "'");
     camera_ = std::make_shared<Camera>(400, 400, fov);
@@ -286,5 +312,25 @@ class SynthSceneBuilder : public SceneBuilder {
   std::shared_ptr<Camera> getCamera() override { return camera_; }
   HostMedium getMedium() override { return medium_; }
 };
+
+// ConfigParser.cpp:84-103 + Main.cpp:64-93: the scene type ("Auto" = by file extension) picks the builder.
+// `resolved` receives the type that was used ("Raw" | "MitsubaXml" | "Vdb" | "Synth").
+inline std::unique_ptr<SceneBuilder> makeSceneBuilder(const std::string& scene_file, std::string type = "Auto",
+                                                      std::string* resolved = nullptr) {
+  if (scene_file.rfind("synth:", 0) == 0) {
+    type = "Synth";
+  } else if (type == "Auto") {
+    size_t dot = scene_file.find_last_of('.');
+    std::string ext = dot == std::string::npos ? "" : scene_file.substr(dot + 1);
+    std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
+    type = ext == "xml" ? "MitsubaXml" : ext == "vdb" ? "Vdb" : "Raw";
+  }
+  if (resolved) *resolved = type;
+  if (type == "MitsubaXml") return std::make_unique<XmlSceneBuilder>(scene_file);
+  if (type == "Vdb") return std::make_unique<VDBSceneBuilder>(scene_file);
+  if (type == "Raw") return std::make_unique<RawSceneBuilder>(scene_file);
+  if (type == "Synth") return std::make_unique<SynthSceneBuilder>(scene_file);
+  throw std::runtime_error("Error: scene type not correct");
+}
 
 }  // namespace cvrhost

@@ -17,44 +17,50 @@ from . import abi
 from .launcher import Scene
 
 
+def load(path: str, scene_type: str = "Auto", name: str | None = None) -> Scene:
+    """SceneAssembler::getScene over the C++ SceneBuilders (cvr_scene_file_load, include/cvr_abi.h): the ONE
+    implementation of the reference's loaders (RawSceneBuilder.h:35-140, XmlSceneBuilder.h:39-266,
+    VDBSceneBuilder.h:40-80) and of the stand-in parameter tables above; this module only wraps the result.
+    scene_type as ConfigParser.cpp:84-103: "Auto" (by extension) | "Raw" | "MitsubaXml" | "Vdb"."""
+    d = abi.load_scene_file(path, scene_type)
+    return Scene(d["density"], d["albedo"], d["box_min"], d["box_max"], scale=d["scale"], max_density=d["max_density"],
+                 fov_x=d["fov_x"], albedo_const=d["albedo_const"], hg_g=d["hg_g"], ggx_alpha=d["ggx_alpha"],
+                 ggx_eta=d["ggx_eta"], name=name or path.rsplit("/", 1)[-1])
+
+
+def _synth(name: str, dims=None, seed: int = 0) -> Scene:
+    spec = f"synth:{name}"
+    if dims is not None:
+        spec += ":" + "x".join(str(int(v)) for v in dims)
+    if seed:
+        spec += f":seed={int(seed)}"
+    return load(spec, name=name)
+
+
 def bucky(seed: int = 0) -> Scene:
-    den, alb, mx = abi.synth_volume("bucky", 32, 32, 32, seed)
-    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=40.0, max_density=mx, fov_x=0.7, name="bucky")
+    return _synth("bucky", None, seed)
 
 
 def hetvol(seed: int = 0, dims=(128, 128, 50)) -> Scene:
-    den, alb, mx = abi.synth_volume("hetvol", dims[0], dims[1], dims[2], seed)
-    return Scene(den, alb, (-0.64, -0.64, -0.25), (0.64, 0.64, 0.25), scale=800.0, max_density=mx,
-                 fov_x=0.33, name="hetvol")
+    return _synth("hetvol", dims, seed)
 
 
 def manix(seed: int = 0, dims=(256, 230, 256)) -> Scene:
-    den, alb, mx = abi.synth_volume("manix", dims[0], dims[1], dims[2], seed)
-    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=mx, fov_x=0.7, name="manix")
+    return _synth("manix", dims, seed)
 
 
 def fbm(n: int = 256, seed: int = 0, albedo: float = 0.99) -> Scene:
-    den, _, mx = abi.synth_volume("fbm", n, n, n, seed, with_albedo=False)
-    return Scene(den, None, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=mx, fov_x=0.7,
-                 albedo_const=(albedo,) * 3, name=f"fbm{n}")
+    sc = _synth("fbm", (n, n, n), seed)
+    sc.albedo_const = (float(albedo),) * 3
+    sc.name = f"fbm{n}"
+    return sc
 
 
 def from_vdb(path: str) -> Scene:
     """VDBSceneBuilder (VDBSceneBuilder.h:40-80): density FloatGrid + albedo Vec3SGrid densified
     over the density grid's active bounding box, max_density = max voxel, the file's world
     box read and ignored (box fixed to +-0.5, Q4), scale 100, default camera (fov 0.7)."""
-    from .vdb import VdbFile
-
-    with VdbFile(path) as f:
-        den = f.densify("density", inactive=(0.0, 0.0, 0.0))
-        alb_grid = f.grid("albedo")  # raises "VDB file does not contain an albedo grid"
-        if alb_grid["dim"] != f.grid("density")["dim"]:
-            # the reference indexes the albedo array with the ALBEDO box but sizes the volume with
-            # the DENSITY resolution (VDBSceneBuilder.h:47-67): only defined when they agree
-            raise abi.CvrError("density and albedo grids have different active bounding boxes")
-        alb = f.densify("albedo", out_channels=4, inactive=(0.0, 0.0, 0.0))
-    return Scene(den, alb, (-0.5,) * 3, (0.5,) * 3, scale=100.0, max_density=float(den.max()), fov_x=0.7,
-                 name=path.rsplit("/", 1)[-1])
+    return load(path, "Vdb")
 
 
 def sparse_from_vdb(path: str, albedo_const=(1.0, 1.0, 1.0)):

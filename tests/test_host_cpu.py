@@ -56,6 +56,43 @@ def test_raw_loader_matches_reference_arithmetic(cli, tmp_path):
     assert rc == 1 and "Error" in err
 
 
+def test_python_scenes_go_through_the_cpp_loaders(cli, tmp_path):
+    """cvr_scene_file_load (include/cvr_abi.h): the ctypes layer loads scenes through the C++ SceneBuilders of
+    cvr_render -- one implementation of the loaders.  Raw file: the exact voxels RawSceneBuilder.h:54-64 produces;
+    stand-ins: the spec grammar, shapes and medium parameters; errors carry the loader's message."""
+    from cudavolumerenderer_b200 import abi, scenes
+
+    rng = np.random.default_rng(9)
+    raw = rng.integers(0, 200, 32 ** 3, dtype=np.uint8)
+    f = tmp_path / "vol.raw"
+    raw.tofile(f)
+    sc = scenes.load(str(f))
+    den = raw.astype(np.float32) / np.float32(raw.max())
+    assert sc.density.shape == (32, 32, 32) and np.array_equal(sc.density.ravel(), den)
+    assert sc.albedo.shape == (32, 32, 32, 4) and np.all(sc.albedo[..., 3] == 1.0)
+    assert (sc.scale, sc.max_density, sc.box_min, sc.box_max) == (40.0, 1.0, (-0.5,) * 3, (0.5,) * 3)
+    assert abs(sc.fov_x - 0.7) < 1e-7 and abs(sc.ggx_eta - float(np.float32(1.05) / np.float32(1.01))) < 1e-7
+    info = abi.load_scene_file(str(f), "Raw")
+    assert info["type"] == "Raw" and info["resolution"] == (400, 400)
+    # the stand-ins: same voxels as the generator called directly, parameters from the ONE table in SceneBuilders.h
+    het = scenes.hetvol(dims=(24, 20, 10), seed=3)
+    d0, a0, mx = abi.synth_volume("hetvol", 24, 20, 10, 3)
+    assert np.array_equal(het.density, d0) and np.array_equal(het.albedo, a0) and het.max_density == mx
+    f32 = lambda t: tuple(float(np.float32(v)) for v in t)  # the medium box travels as fp32 (cvr_scene_desc)
+    assert (het.scale, het.box_min, het.box_max) == (800.0, f32((-0.64, -0.64, -0.25)), f32((0.64, 0.64, 0.25)))
+    assert abs(het.fov_x - 0.33) < 1e-7
+    fb = scenes.fbm(16)
+    assert fb.albedo is None and fb.albedo_const == (0.99, 0.99, 0.99) and fb.density.shape == (16, 16, 16) and fb.name == "fbm16"
+    assert abs(abi.load_scene_file("synth:fbm:16")["albedo_const"][0] - 0.99) < 1e-7
+    assert scenes.manix(dims=(12, 10, 8)).density.shape == (8, 10, 12) and scenes.bucky().density.shape == (32, 32, 32)
+    for bad, msg in ((str(tmp_path / "missing.raw"), "Error opening file"), ("synth:nosuch", "unknown synthetic scene"),
+                     ("synth:fbm:abc", "cannot parse"), (str(tmp_path / "missing.vdb"), "OpenVDB error")):
+        with pytest.raises(abi.CvrError, match=msg):
+            scenes.load(bad)
+    with pytest.raises(abi.CvrError, match="scene type not correct"):
+        scenes.load(str(f), "Obj")
+
+
 def write_vol(path, data, box):
     nz, ny, nx = data.shape[:3]
     ch = 1 if data.ndim == 3 else data.shape[3]

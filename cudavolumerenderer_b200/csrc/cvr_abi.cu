@@ -1512,11 +1512,21 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
       if (launch(h, h->d_tile, r->res_x, 1, h->d_origins, n_mine, ph.tile_first, ph.tile_stride, seed0, seed_step, nullptr, pb, pe))
         return 1;
     }
-    for (uint32_t k = 0; k < n_tiles; ++k) {
-      if (!owned(k)) continue;
-      uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
-      k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, ox, oy,
-                                                d_image, r->res_x, ox, oy, scale);
+    if (n_phases <= 2 && n_tiles <= 65535u) {
+      ResolveOwner own{};
+      own.n = (uint32_t)n_phases;
+      for (int i = 0; i < n_phases; ++i)
+        own.first[i] = phases[i].tile_first, own.stride[i] = phases[i].tile_stride, own.limit[i] = std::min(phases[i].tile_limit, n_tiles);
+      const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((tile_px + 255) / 256, ((size_t)h->sm_count * 8 + n_tiles - 1) / n_tiles));
+      k_resolve_tiles<<<dim3(bx, n_tiles), 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, (const uint2*)h->d_origins,
+                                                                 d_image, scale, own);
+    } else {
+      for (uint32_t k = 0; k < n_tiles; ++k) {
+        if (!owned(k)) continue;
+        uint32_t ox = origins[2 * k], oy = origins[2 * k + 1];
+        k_resolve_tile<<<rg, 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, ox, oy,
+                                                  d_image, r->res_x, ox, oy, scale);
+      }
     }
     CVR_CUDA(h, cudaGetLastError());
   } else {
@@ -1631,6 +1641,8 @@ int cvr_render_image_sharded(cvr_handle h, const cvr_render_desc* r, const cvr_s
 #include <dlfcn.h>
 #include <nccl.h>  // types and enums only: the library is loaded with dlopen on first use
 
+#include <map>
+#include <mutex>
 #include <thread>
 
 struct cvr_group {
@@ -1700,10 +1712,25 @@ NcclApi& nccl_api() {
   return api;
 }
 
+// ncclCommInitAll over 8 devices takes ~1.1 s: communicators outlive their group and are handed to the next group over
+// the same device list (cvr_render builds a renderer per trial, Main.cpp runTest; measured before this cache: 1.20 s
+// "rendering time" per trial on 8 GPUs against 0.108 s on one -- all of it communicator set-up inside the first reduce)
+std::mutex g_comm_cache_mutex;
+std::map<std::vector<int>, std::vector<std::vector<ncclComm_t>>> g_comm_cache;
+
 int group_comms(cvr_group_handle g) {
   if (!g->comms.empty()) return 0;
   NcclApi& N = nccl_api();
   if (!N.lib) return gfail(g, "cvr_group: %s (groups of more than one device need NCCL)", N.why.c_str());
+  {
+    std::lock_guard<std::mutex> lock(g_comm_cache_mutex);
+    auto it = g_comm_cache.find(g->devices);
+    if (it != g_comm_cache.end() && !it->second.empty()) {
+      g->comms = std::move(it->second.back());
+      it->second.pop_back();
+      return 0;
+    }
+  }
   g->comms.assign(g->members.size(), nullptr);
   ncclResult_t rc = N.CommInitAll(g->comms.data(), (int)g->members.size(), g->devices.data());
   if (rc != ncclSuccess) {
@@ -1766,6 +1793,11 @@ int cvr_group_create(const char* kernel_name, const int* devices, int n_devices,
     g->devices.push_back(dev);
     g->d_images.push_back(nullptr);
   }
+  if (n_devices > 1 && group_comms(g)) {  // set-up cost and a missing NCCL belong to create, not to the first render
+    std::string msg = g->err;
+    cvr_group_destroy(g);
+    return gfail(nullptr, "cvr_group_create: %s", msg.c_str());
+  }
   *out = g;
   return 0;
 }
@@ -1773,9 +1805,13 @@ int cvr_group_create(const char* kernel_name, const int* devices, int n_devices,
 int cvr_group_destroy(cvr_group_handle g) {
   if (!g) return 0;
   if (!g->comms.empty()) {
-    NcclApi& N = nccl_api();
-    for (ncclComm_t c : g->comms)
-      if (c && N.lib) N.CommDestroy(c);
+    // quiesce, then park the communicators for the next group over the same devices (group_comms)
+    for (size_t r = 0; r < g->members.size(); ++r) {
+      cudaSetDevice(g->devices[r]);
+      cudaStreamSynchronize(g->members[r]->stream);
+    }
+    std::lock_guard<std::mutex> lock(g_comm_cache_mutex);
+    g_comm_cache[g->devices].push_back(std::move(g->comms));
   }
   for (size_t r = 0; r < g->members.size(); ++r) {
     if (g->d_images[r]) {
@@ -1897,6 +1933,7 @@ int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int 
   std::vector<void*> bufs((size_t)n);
   for (int r = 0; r < n; ++r) bufs[(size_t)r] = g->d_images[(size_t)r];
   if (d_image_rank0_out) bufs[0] = d_image_rank0_out;
+  PhaseTimer pt("cvr_group_render_image");
   // every rank renders its share into its own zeroed full-resolution image (one host thread each)
   if (int bad = for_each_member(g, [&](int r) {
         RenderPhase ph[2];
@@ -1910,8 +1947,16 @@ int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int 
         return render_phases(g->members[(size_t)r], desc, ph, np, nullptr, bufs[(size_t)r], true, false);
       }))
     return member_failed(g, bad, "cvr_group_render_image");
+  pt.mark("renders enqueued");
   if (n > 1) {
     if (cvr_group_reduce(g, bufs.data(), (uint64_t)image_px * 4)) return 1;
+    pt.mark("renders + reduce done");
+    // alpha is "some path escaped" / iterations, not a sum over the ranks that saw one (k_clamp_alpha)
+    cudaSetDevice(g->devices[0]);
+    k_clamp_alpha<<<g->members[0]->sm_count * 4, 256, 0, g->members[0]->stream>>>((float4*)bufs[0], image_px,
+                                                                                   1.0f / (float)desc->iterations);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: alpha: %s", cudaGetErrorString(e));
   }
   if (host_image) {
     // the covered region (tile_dim * n_tiles; Q6: remainder pixels are never rendered and left untouched)
@@ -1928,6 +1973,7 @@ int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int 
     cudaError_t e = cudaStreamSynchronize(g->members[(size_t)r]->stream);
     if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
   }
+  pt.mark("image on the host, streams idle");
   return 0;
 }
 

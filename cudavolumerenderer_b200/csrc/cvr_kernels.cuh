@@ -1908,6 +1908,15 @@ __global__ void k_build_skip_table(const float* __restrict__ maj, uint32_t mx, u
   out[i] = (uint8_t)((int)q - 1);
 }
 
+// After the framebuffers of several devices were summed: the alpha channel is not a sum.  A path that escapes STORES
+// w = 1 (Utilities.cuh:15-22, Q12) and the resolve divides by the iteration count, so a pixel's alpha is 1 / iterations
+// if any of its paths escaped and 0 otherwise; sample-sharded ranks each contribute that value, and the sum counts the
+// ranks.  min(sum, 1 / iterations) restores exactly what one device produces.
+__global__ void k_clamp_alpha(float4* __restrict__ image, size_t n_px, float limit) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_px; i += (size_t)gridDim.x * blockDim.x)
+    image[i].w = fminf(image[i].w, limit);
+}
+
 __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w, uint32_t tile_h,
                                uint32_t in_stride, uint32_t in_off_x, uint32_t in_off_y,
                                float4* __restrict__ image, uint32_t full_w, uint32_t off_x,
@@ -1918,6 +1927,30 @@ __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w,
     float4 v = tile[(size_t)(y + in_off_y) * in_stride + (x + in_off_x)];
     v.x = v.x / scale, v.y = v.y / scale, v.z = v.z / scale, v.w = v.w / scale;
     image[(size_t)(y + off_y) * full_w + (x + off_x)] = v;
+  }
+}
+
+// The fused-tiles form of the resolve: ONE launch over every tile of the table (blockIdx.y = tile number), tiles this
+// rank does not own (up to two interleave phases, cvr_shard) are skipped.  100 launches of k_resolve_tile per C3 image
+// were 1.0-1.5 ms of host time per render -- serialised on the driver lock when 8 host threads render for a device group.
+struct ResolveOwner {
+  uint32_t n, first[2], stride[2], limit[2];
+};
+__global__ void k_resolve_tiles(const float4* __restrict__ accum, uint32_t tile_w, uint32_t tile_h, uint32_t full_w,
+                                const uint2* __restrict__ origins, float4* __restrict__ image, float scale, ResolveOwner own) {
+  const uint32_t k = blockIdx.y;
+  bool mine = false;
+  for (uint32_t p = 0; p < own.n; ++p)
+    mine |= k >= own.first[p] && k < own.limit[p] && (k - own.first[p]) % own.stride[p] == 0;
+  if (!mine) return;
+  const uint2 o = origins[k];
+  const uint32_t n = tile_w * tile_h;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t x = i % tile_w, y = i / tile_w;
+    const size_t at = (size_t)(y + o.y) * full_w + (x + o.x);
+    float4 v = accum[at];
+    v.x = v.x / scale, v.y = v.y / scale, v.z = v.z / scale, v.w = v.w / scale;
+    image[at] = v;
   }
 }
 

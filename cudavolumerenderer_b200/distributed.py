@@ -10,7 +10,8 @@ Sharding rules (the library's planner, cvr_shard_plan; pure functions, tested on
   balanced: the complete rounds of the tile interleave by tile, the n_tiles mod G left-over
             tiles by sample index: every rank renders n_tiles / G tile-equivalents (100 tiles on
             8 ranks: 12.5 each instead of 13 / 12).
-Every rank resolves with scale = TOTAL iterations, so the sum over ranks is the image.
+Every rank resolves with scale = TOTAL iterations, so the sum over ranks is the image (rgb; the alpha channel,
+"some path of this pixel escaped" / iterations, is clamped back to that value after the sum).
 The one-process form of the same thing (N devices, one host thread each, ncclReduce called by
 the library itself) is cudavolumerenderer_b200.DeviceGroup / cvr_group_render_image.
 """
@@ -75,4 +76,11 @@ def render_sharded(launcher, res, n_tiles, iterations: int, mode: str, d_image, 
             dist.all_reduce(d_image)
         else:
             dist.reduce(d_image, dst=reduce_to)
+        if reduce_to is None or reduce_to == rank:
+            # alpha is not a sum: an escaping path STORES w = 1 (Q12) and the resolve divides by the iteration count, so
+            # every sample-sharded rank contributes 1 / iterations where one of ITS paths escaped (k_clamp_alpha in the
+            # library's own group path); min(sum, 1 / iterations) is what one device produces
+            import numpy as np
+
+            d_image[..., 3].clamp_(max=float(np.float32(1.0) / np.float32(iterations)))
     return d_image

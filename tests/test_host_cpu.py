@@ -193,6 +193,8 @@ class FakeLauncher:
         for s in range(sample_first, sample_first + count):
             acc += ((xs * 31 + ys * 17 + s * 7) % 13) / 13.0
         img[..., 0] += torch.from_numpy(np.where(mine, acc / iterations, 0.0).astype(np.float32))
+        # alpha as the kernels leave it: an escaping path STORES w = 1, the resolve divides by the iteration count
+        img[..., 3] += torch.from_numpy(np.where(mine & (count > 0), np.float32(1) / np.float32(iterations), 0).astype(np.float32))
 
     def renderImageSharded(self, res, n_tiles, iterations, shard, fov_x=0.7, inv_view=None, fuse_tiles=True,
                            host_image=None, d_image=None):
@@ -211,6 +213,8 @@ class FakeLauncher:
             in_tail = shard.sample_first <= s < shard.sample_first + shard.sample_count
             acc += np.where(whole | (tail & in_tail), v, 0.0)
         IMG[..., 0] += torch.from_numpy((acc / iterations).astype(np.float32))
+        seen = whole | (tail & (shard.sample_count > 0))
+        IMG[..., 3] += torch.from_numpy(np.where(seen, np.float32(1) / np.float32(iterations), 0).astype(np.float32))
 
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["CVR_PORT"],
                         rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
@@ -256,6 +260,9 @@ def test_world_size_2_gloo_reduction(tmp_path):
     for mode in ("spp", "tiles", "balanced", "balanced33"):
         assert np.allclose(outs[1][mode], outs[2][mode], atol=1e-6), mode
         assert outs[1][mode][..., 0].sum() > 0
+        # alpha is not a sum over the sample-sharded ranks: 1 / iterations wherever a path was traced, exactly
+        assert np.array_equal(outs[1][mode][..., 3], outs[2][mode][..., 3]), mode
+        assert set(np.unique(outs[2][mode][..., 3])) <= {np.float32(0), np.float32(1) / np.float32(7 if mode == "balanced33" else 10)}
     assert np.allclose(outs[1]["spp"], outs[1]["balanced"], atol=1e-6)
 
 

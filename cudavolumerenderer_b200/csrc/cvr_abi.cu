@@ -366,8 +366,11 @@ void free_volume(cvr_handle h) {
 
 int ensure_allocated(cvr_handle h) {
   if (h->allocated) return 0;
-  CVR_CUDA(h, cudaMalloc(&h->d_head, sizeof(unsigned long long)));
-  CVR_CUDA(h, cudaMalloc(&h->d_ctr, sizeof(DeviceCounters)));
+  // stream-ordered pool (like the volumes): a renderer built per trial (cvr_render, the reference's runTest) then
+  // costs no cudaMalloc -- five of them per handle, serialised across the 8 host threads of a device group, were
+  // 17 ms of a 29 ms C3 render on 8 GPUs
+  CVR_CUDA(h, cudaMallocAsync((void**)&h->d_head, sizeof(unsigned long long), h->stream));
+  CVR_CUDA(h, cudaMallocAsync((void**)&h->d_ctr, sizeof(DeviceCounters), h->stream));
   CVR_CUDA(h, cudaMemsetAsync(h->d_head, 0, sizeof(unsigned long long), h->stream));
   CVR_CUDA(h, cudaMemsetAsync(h->d_ctr, 0, sizeof(DeviceCounters), h->stream));
   h->allocated = true;
@@ -714,11 +717,9 @@ int cvr_release(cvr_handle h) {
   free_volume(h);
   vol_flush_parked(h);
   cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_head);
-  cudaFree(h->d_ctr);
-  cudaFree(h->d_tile);
-  cudaFree(h->d_image);
-  cudaFree(h->d_origins);
+  for (void* p : {(void*)h->d_head, (void*)h->d_ctr, (void*)h->d_tile, (void*)h->d_image, (void*)h->d_origins})
+    if (p) cudaFreeAsync(p, h->stream);
+  cudaStreamSynchronize(h->stream);
   h->d_head = nullptr, h->d_ctr = nullptr, h->d_tile = nullptr, h->d_image = nullptr;
   h->d_origins = nullptr;
   h->d_tile_px = h->d_image_px = h->d_origins_n = 0;
@@ -907,7 +908,14 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
 
 int cvr_set_stream(cvr_handle h, void* cuda_stream) {
   CVR_CHECK_HANDLE(h);
-  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  if (next != h->stream) {
+    // the handle's buffers come from the stream-ordered pool: what was allocated (or freed) in the order of the old
+    // stream must be settled before the new one touches it
+    if (set_device(h)) return 1;
+    cudaStreamSynchronize(h->stream);
+  }
+  h->stream = next;
   return 0;
 }
 
@@ -1457,9 +1465,10 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
   const size_t image_px = (size_t)r->res_x * r->res_y;
   const size_t tile_px = (size_t)tile_dim[0] * tile_dim[1];
   if (h->d_image_px < image_px) {
-    cudaFree(h->d_image);
+    if (h->d_image) cudaFreeAsync(h->d_image, h->stream);
+    h->d_image = nullptr;
     h->d_image_px = 0;
-    CVR_CUDA(h, cudaMalloc(&h->d_image, image_px * sizeof(float4)));
+    CVR_CUDA(h, cudaMallocAsync((void**)&h->d_image, image_px * sizeof(float4), h->stream));
     h->d_image_px = image_px;
   }
   float4* d_image = d_image_out ? (float4*)d_image_out : h->d_image;
@@ -1486,15 +1495,17 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
     // one launch per phase over every tile it owns, accumulating straight into a full-resolution
     // buffer; same pixels, same streams as the loop below
     if (h->d_tile_px < image_px) {
-      cudaFree(h->d_tile);
+      if (h->d_tile) cudaFreeAsync(h->d_tile, h->stream);
+      h->d_tile = nullptr;
       h->d_tile_px = 0;
-      CVR_CUDA(h, cudaMalloc(&h->d_tile, image_px * sizeof(float4)));
+      CVR_CUDA(h, cudaMallocAsync((void**)&h->d_tile, image_px * sizeof(float4), h->stream));
       h->d_tile_px = image_px;
     }
     if (h->d_origins_n < n_tiles) {
-      cudaFree(h->d_origins);
+      if (h->d_origins) cudaFreeAsync(h->d_origins, h->stream);
+      h->d_origins = nullptr;
       h->d_origins_n = 0;
-      CVR_CUDA(h, cudaMalloc(&h->d_origins, n_tiles * sizeof(uint2)));
+      CVR_CUDA(h, cudaMallocAsync((void**)&h->d_origins, n_tiles * sizeof(uint2), h->stream));
       h->d_origins_n = n_tiles;
     }
     CVR_CUDA(h, cudaMemcpyAsync(h->d_origins, origins.data(), n_tiles * sizeof(uint2),
@@ -1531,9 +1542,10 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
     CVR_CUDA(h, cudaGetLastError());
   } else {
     if (h->d_tile_px < tile_px) {
-      cudaFree(h->d_tile);
+      if (h->d_tile) cudaFreeAsync(h->d_tile, h->stream);
+      h->d_tile = nullptr;
       h->d_tile_px = 0;
-      CVR_CUDA(h, cudaMalloc(&h->d_tile, tile_px * sizeof(float4)));
+      CVR_CUDA(h, cudaMallocAsync((void**)&h->d_tile, tile_px * sizeof(float4), h->stream));
       h->d_tile_px = tile_px;
     }
     for (int i = 0; i < n_phases; ++i) {
@@ -1816,7 +1828,7 @@ int cvr_group_destroy(cvr_group_handle g) {
   for (size_t r = 0; r < g->members.size(); ++r) {
     if (g->d_images[r]) {
       cudaSetDevice(g->devices[r]);
-      cudaFree(g->d_images[r]);
+      cudaFreeAsync(g->d_images[r], g->members[r]->stream);
     }
     cvr_destroy(g->members[r]);
   }
@@ -1920,9 +1932,9 @@ int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int 
   if (g->image_px < image_px) {
     for (int r = 0; r < n; ++r) {
       cudaSetDevice(g->devices[(size_t)r]);
-      cudaFree(g->d_images[(size_t)r]);
+      if (g->d_images[(size_t)r]) cudaFreeAsync(g->d_images[(size_t)r], g->members[(size_t)r]->stream);
       g->d_images[(size_t)r] = nullptr;
-      cudaError_t e = cudaMalloc(&g->d_images[(size_t)r], image_px * sizeof(float4));
+      cudaError_t e = cudaMallocAsync((void**)&g->d_images[(size_t)r], image_px * sizeof(float4), g->members[(size_t)r]->stream);
       if (e != cudaSuccess) {
         g->image_px = 0;
         return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));

@@ -25,8 +25,9 @@ roofline   dominant kernel k_volpt_warp.  `achieved` / `frac` keep SURVEY.md 8(d
            random-sector gather peak at that footprint is the utilisation figure), "hbm" beyond.
 configs    the same measurement for C3 (MANIX 1024^2 x 256 spp, 10x10 tiles: north_star's target)
            and C4 (fBm 1024^3, 2048^2 x 128 spp: the HBM-resident dense volume), N = 1 only.
-strong_scaling  C3 with the image and spp FIXED, tiles + samples sharded over the N ranks with the
-           balanced plan (cvr_shard_plan) and ONE reduce to rank 0, device-timed, max over ranks.
+strong_scaling  C3 with the image and spp FIXED, sharded over the N ranks with the balanced plan
+           (cvr_shard_plan: the sample split, since 256 spp divide evenly) and ONE reduce to rank 0,
+           device-timed, max over ranks.
 cpu_baseline  the reference's OWN regenerationSK kernel (d_render_single_thread_regeneration
            and everything it calls) compiled for the host by g++ from the reference's headers
            (oracle/_ref/libcvr_ref_cpu.so, kind "reference": one persistent CUDA thread per host
@@ -486,7 +487,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ctr3 = kl.counters()
     c3_paths = 102 * 102 * 100 * C3_SPP  # Q6: 10 x 10 tiles of 102^2 cover 1020^2 pixels
     strong = {"workload": "C3 MANIX-like 256x230x256 (procedural stand-in), 1024x1024, 256 spp, 10x10 tiles (1020^2 pixels covered), regenerationSK",
-              "scaling": "strong", "n_gpus": world, "sharding": "balanced (cvr_shard_plan: whole rounds of tiles by rank, left-over tiles by sample index), one reduce to rank 0",
+              "scaling": "strong", "n_gpus": world, "sharding": "balanced (cvr_shard_plan: 256 samples over N ranks = the sample split, every rank traces the same number of paths through every tile in one launch), one reduce to rank 0",
               "ms_per_step": ms_c3, "value": c3_paths / ms_c3 / 1e3, "unit": METRIC, "steps": n_c3,
               "image_mean": float(torch.nanmean(d_img3[:1020, :1020, :3]).item()) if rank == 0 else None}
 

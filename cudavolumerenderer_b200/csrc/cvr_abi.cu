@@ -1624,6 +1624,14 @@ int cvr_shard_plan(uint32_t n_tiles, uint32_t iterations, int rank, int world, i
     out->tile_first = out->tile_limit = 0, out->tile_stride = 1;  // no whole tiles
     out->tail_first = 0, out->tail_limit = n_tiles;
     out->sample_first = s_first, out->sample_count = s_count;
+  } else if (rem == 0) {
+    // the samples divide evenly: the sample split IS the balanced plan -- every rank traces exactly the same number of
+    // paths through the same pixels in ONE launch.  Measured, C3 on 8 ranks, per-rank kernel ms (tools/shard_balance.py,
+    // ideal 10.46): sample split 10.86-10.88, tile interleave 10.52-10.95 (tiles are unequal work), rounds of tiles +
+    // left-over tiles by sample 10.73-11.15 (two launches = two drain tails of ~0.4 ms).
+    out->tile_first = out->tile_limit = 0, out->tile_stride = 1;
+    out->tail_first = 0, out->tail_limit = n_tiles;
+    out->sample_first = s_first, out->sample_count = s_count;
   } else {
     const uint32_t whole = (n_tiles / w) * w;
     out->tile_first = r, out->tile_stride = w, out->tile_limit = whole;

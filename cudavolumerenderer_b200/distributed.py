@@ -7,9 +7,9 @@ Sharding rules (the library's planner, cvr_shard_plan; pure functions, tested on
             pixels, the image does not depend on G.
   spp:      rank r renders sample indices [first, first+count) of every pixel; stream ids
             are seed + sample*npix + pixel, so the multiset of paths equals the 1-GPU run.
-  balanced: the complete rounds of the tile interleave by tile, the n_tiles mod G left-over
-            tiles by sample index: every rank renders n_tiles / G tile-equivalents (100 tiles on
-            8 ranks: 12.5 each instead of 13 / 12).
+  balanced: equal work on every rank: the sample split when iterations is a multiple of G (one launch, the
+            same number of paths through the same pixels on every rank); otherwise the complete rounds of the
+            tile interleave by tile and the n_tiles mod G left-over tiles by sample index.
 Every rank resolves with scale = TOTAL iterations, so the sum over ranks is the image (rgb; the alpha channel,
 "some path of this pixel escaped" / iterations, is clamped back to that value after the sum).
 The one-process form of the same thing (N devices, one host thread each, ncclReduce called by

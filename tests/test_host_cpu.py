@@ -269,7 +269,8 @@ def test_world_size_2_gloo_reduction(tmp_path):
 def test_shard_plans_cover_every_tile_sample_pair_once():
     """cvr_shard_plan (C ABI): over all ranks every (tile, sample) pair is rendered exactly once in
     every mode, and the balanced mode gives every rank the same amount of work up to one sample of
-    the tail tiles (100 tiles on 8 ranks: 12 whole tiles + 1/8 of 4 tiles each)."""
+    the tail tiles (100 tiles x 250 samples on 8 ranks: 12 whole tiles + a share of 4 tiles each; 256 samples:
+    32 samples of every tile each)."""
     from cudavolumerenderer_b200 import abi
 
     for n_tiles, iters in ((100, 256), (1, 64), (64, 16), (9, 7), (5, 3), (7, 1)):
@@ -290,9 +291,13 @@ def test_shard_plans_cover_every_tile_sample_pair_once():
                 assert np.all(cover == 1), (n_tiles, iters, world, mode)
                 if mode == "balanced":
                     assert max(work) - min(work) <= n_tiles % world, (n_tiles, iters, world, work)
+    # samples divide evenly -> the sample split (same paths on every rank, one launch) ...
     sh = abi.shard_plan(100, 256, 3, 8, "balanced")
+    assert (sh.tile_first, sh.tile_limit, sh.tail_first, sh.tail_limit, sh.sample_first, sh.sample_count) == (0, 0, 0, 100, 96, 32)
+    # ... otherwise whole rounds of tiles by rank and the left-over tiles by sample index
+    sh = abi.shard_plan(100, 250, 3, 8, "balanced")
     assert (sh.tile_first, sh.tile_stride, sh.tile_limit, sh.tail_first, sh.tail_limit, sh.sample_first, sh.sample_count) == \
-        (3, 8, 96, 96, 100, 96, 32)
+        (3, 8, 96, 96, 100, 95, 31)
     with pytest.raises(ValueError):
         abi.shard_plan(10, 4, 2, 2, "balanced")
     with pytest.raises(ValueError):

@@ -561,7 +561,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / n_e2e},
-        "gpu_launches": launches,
+        "gpu_launches": 2 * launches,
+        "gpu_launches_what": f"rank 0, timed region: {launches} x k_volpt_warp (the path kernel, counted by the library) + "
+                             f"{launches} x k_resolve_tiles (one fused resolve per render); the L2 flush fill and the image "
+                             "zero fill are torch kernels and not counted",
         "roofline": roofline,
         "configs": configs,
         "strong_scaling": strong,

@@ -538,7 +538,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         configs = [c3, c4]
         kl.setScene(sc)
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
-        cpu_spp = 16
+        # ~10-15 s of CPU work: the whole 64 spp on a 32-core box (5 Msamples/s), half of them on 16 cores (2.6 Msamples/s)
+        cpu_spp = SPP if (os.cpu_count() or 1) >= 32 else SPP // 2
         v, cores, dt, _, kind, what = cpu_sample(sc, cpu_spp)
         cpu = {"value": v, "unit": METRIC, "cores": cores, "kind": kind,
                "sample": f"{RES}x{RES} at {cpu_spp} spp ({dt:.1f} s), {what}"}

@@ -1437,8 +1437,9 @@ bool phase_owns(const RenderPhase& ph, uint32_t k) {
 
 // CudaVolPath::render (CudaVolPath.cpp:338-347) over the given phases.  `zero_image`: clear the
 // resolved image first (multi-GPU: every rank contributes a full-resolution image to a sum).
+// `add_into_image`: the resolve ADDS into d_image_out (which may be another device's memory) instead of storing (device groups).
 int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* phases, int n_phases, float* host_image,
-                  void* d_image_out, bool zero_image, bool sync_at_end) {
+                  void* d_image_out, bool zero_image, bool sync_at_end, bool add_into_image = false) {
   if (!r) return fail(h, "cvr_render_image: null desc");
   if (!r->res_x || !r->res_y || !r->n_tiles_x || !r->n_tiles_y || !r->iterations)
     return fail(h, "cvr_render_image: zero resolution / tiles / iterations");
@@ -1491,6 +1492,8 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
         if (phase_owns(phases[i], k) && phase_owns(phases[j], k)) return fail(h, "cvr_render_image: phases share tile %u", k);
   }
 
+  if (add_into_image && !(r->fuse_tiles && n_phases <= 2 && n_tiles <= 65535u))
+    return fail(h, "cvr_render_image: the adding resolve needs fuse_tiles, at most two phases and at most 65535 tiles");
   if (r->fuse_tiles) {
     // one launch per phase over every tile it owns, accumulating straight into a full-resolution
     // buffer; same pixels, same streams as the loop below
@@ -1529,8 +1532,12 @@ int render_phases(cvr_handle h, const cvr_render_desc* r, const RenderPhase* pha
       for (int i = 0; i < n_phases; ++i)
         own.first[i] = phases[i].tile_first, own.stride[i] = phases[i].tile_stride, own.limit[i] = std::min(phases[i].tile_limit, n_tiles);
       const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((tile_px + 255) / 256, ((size_t)h->sm_count * 8 + n_tiles - 1) / n_tiles));
-      k_resolve_tiles<<<dim3(bx, n_tiles), 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x, (const uint2*)h->d_origins,
-                                                                 d_image, scale, own);
+      if (add_into_image)
+        k_resolve_tiles<true><<<dim3(bx, n_tiles), 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x,
+                                                                         (const uint2*)h->d_origins, d_image, scale, own);
+      else
+        k_resolve_tiles<false><<<dim3(bx, n_tiles), 256, 0, h->stream>>>(h->d_tile, tile_dim[0], tile_dim[1], r->res_x,
+                                                                          (const uint2*)h->d_origins, d_image, scale, own);
     } else {
       for (uint32_t k = 0; k < n_tiles; ++k) {
         if (!owned(k)) continue;
@@ -1671,6 +1678,15 @@ struct cvr_group {
   std::vector<ncclComm_t> comms;     // empty until the first reduce of a group with > 1 device
   std::vector<float4*> d_images;     // per-member full-resolution resolved image (group-owned)
   size_t image_px = 0;
+  // "peer" reduce: every device adds its resolved share straight into d_peer_image on the first device through NVLink
+  // peer memory (k_resolve_tiles<true>); ordered by events instead of a collective.  Needs peer access from every
+  // member to the first; otherwise (or with the option group_reduce=nccl) the shares are summed by ONE ncclReduce.
+  bool peer_ok = false;
+  int reduce_mode = -1;              // -1 auto (= nccl: measured, below), 0 nccl, 1 peer
+  float4* d_peer_image = nullptr;    // plain cudaMalloc on the first device (pool memory is not peer-mapped by default)
+  size_t peer_image_px = 0;
+  cudaEvent_t ev_zero = nullptr;
+  std::vector<cudaEvent_t> ev_done;
   std::string err;
 };
 
@@ -1813,6 +1829,29 @@ int cvr_group_create(const char* kernel_name, const int* devices, int n_devices,
     g->devices.push_back(dev);
     g->d_images.push_back(nullptr);
   }
+  if (n_devices > 1) {
+    // peer access member -> first device (NVLink / NVSwitch): lets a member's resolve add into the first device's image
+    bool ok = true;
+    for (int r = 1; r < n_devices && ok; ++r) {
+      int can = 0;
+      ok = cudaDeviceCanAccessPeer(&can, g->devices[(size_t)r], g->devices[0]) == cudaSuccess && can;
+      if (ok) {
+        cudaSetDevice(g->devices[(size_t)r]);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(g->devices[0], 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError(), pe = cudaSuccess;
+        ok = pe == cudaSuccess;
+      }
+    }
+    (void)cudaGetLastError();
+    g->peer_ok = ok;
+    g->ev_done.assign((size_t)n_devices, nullptr);
+    for (int r = 0; r < n_devices; ++r) {
+      cudaSetDevice(g->devices[(size_t)r]);
+      cudaEventCreateWithFlags(&g->ev_done[(size_t)r], cudaEventDisableTiming);
+    }
+    cudaSetDevice(g->devices[0]);
+    cudaEventCreateWithFlags(&g->ev_zero, cudaEventDisableTiming);
+  }
   if (n_devices > 1 && group_comms(g)) {  // set-up cost and a missing NCCL belong to create, not to the first render
     std::string msg = g->err;
     cvr_group_destroy(g);
@@ -1833,6 +1872,16 @@ int cvr_group_destroy(cvr_group_handle g) {
     std::lock_guard<std::mutex> lock(g_comm_cache_mutex);
     g_comm_cache[g->devices].push_back(std::move(g->comms));
   }
+  if (!g->devices.empty()) {
+    cudaSetDevice(g->devices[0]);
+    if (g->d_peer_image) cudaFree(g->d_peer_image);
+    if (g->ev_zero) cudaEventDestroy(g->ev_zero);
+  }
+  for (size_t r = 0; r < g->ev_done.size(); ++r)
+    if (g->ev_done[r]) {
+      cudaSetDevice(g->devices[r]);
+      cudaEventDestroy(g->ev_done[r]);
+    }
   for (size_t r = 0; r < g->members.size(); ++r) {
     if (g->d_images[r]) {
       cudaSetDevice(g->devices[r]);
@@ -1859,6 +1908,14 @@ int cvr_group_member(cvr_group_handle g, int rank, cvr_handle* member) {
 
 int cvr_group_set_option(cvr_group_handle g, const char* key, const char* value) {
   if (!g) return gfail(nullptr, "null group");
+  if (key && value && std::string(key) == "group_reduce") {  // how the members' shares are summed: auto | peer | nccl
+    const std::string v(value);
+    if (v != "auto" && v != "peer" && v != "nccl") return gfail(g, "group_reduce: unknown value '%s' (auto | peer | nccl)", value);
+    if (v == "peer" && g->members.size() > 1 && !g->peer_ok)
+      return gfail(g, "group_reduce=peer: device %d has no peer access to device %d", g->devices.back(), g->devices[0]);
+    g->reduce_mode = v == "auto" ? -1 : v == "peer" ? 1 : 0;
+    return 0;
+  }
   for (size_t r = 0; r < g->members.size(); ++r)
     if (cvr_set_option(g->members[r], key, value)) return member_failed(g, (int)r + 1, "cvr_group_set_option");
   return 0;
@@ -1937,45 +1994,91 @@ int cvr_group_render_image(cvr_group_handle g, const cvr_render_desc* desc, int 
     if (cvr_shard_plan(n_tiles, desc->iterations, r, n, shard_mode, &plan[(size_t)r]))
       return gfail(g, "cvr_group_render_image: bad shard mode %d", shard_mode);
   const size_t image_px = (size_t)desc->res_x * desc->res_y;
-  if (g->image_px < image_px) {
-    for (int r = 0; r < n; ++r) {
-      cudaSetDevice(g->devices[(size_t)r]);
-      if (g->d_images[(size_t)r]) cudaFreeAsync(g->d_images[(size_t)r], g->members[(size_t)r]->stream);
-      g->d_images[(size_t)r] = nullptr;
-      cudaError_t e = cudaMallocAsync((void**)&g->d_images[(size_t)r], image_px * sizeof(float4), g->members[(size_t)r]->stream);
-      if (e != cudaSuccess) {
-        g->image_px = 0;
-        return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
-      }
-    }
-    g->image_px = image_px;
-  }
-  std::vector<void*> bufs((size_t)n);
-  for (int r = 0; r < n; ++r) bufs[(size_t)r] = g->d_images[(size_t)r];
-  if (d_image_rank0_out) bufs[0] = d_image_rank0_out;
+  auto phases_of = [&](int r, RenderPhase* ph) {
+    int np = 0;
+    const cvr_shard& sh = plan[(size_t)r];
+    if (sh.tile_first < sh.tile_limit)
+      ph[np++] = RenderPhase{sh.tile_first, sh.tile_stride ? sh.tile_stride : 1u, sh.tile_limit, 0u, kAllSamples};
+    if (sh.tail_first < sh.tail_limit && sh.sample_count)
+      ph[np++] = RenderPhase{sh.tail_first, 1u, sh.tail_limit, sh.sample_first, sh.sample_count};
+    return np;
+  };
   PhaseTimer pt("cvr_group_render_image");
-  // every rank renders its share into its own zeroed full-resolution image (one host thread each)
-  if (int bad = for_each_member(g, [&](int r) {
-        RenderPhase ph[2];
-        int np = 0;
-        const cvr_shard& sh = plan[(size_t)r];
-        if (sh.tile_first < sh.tile_limit)
-          ph[np++] = RenderPhase{sh.tile_first, sh.tile_stride ? sh.tile_stride : 1u, sh.tile_limit, 0u, kAllSamples};
-        if (sh.tail_first < sh.tail_limit && sh.sample_count)
-          ph[np++] = RenderPhase{sh.tail_first, 1u, sh.tail_limit, sh.sample_first, sh.sample_count};
-        // no sync here: the reduce is queued behind the render on the member's stream
-        return render_phases(g->members[(size_t)r], desc, ph, np, nullptr, bufs[(size_t)r], true, false);
-      }))
-    return member_failed(g, bad, "cvr_group_render_image");
-  pt.mark("renders enqueued");
+  std::vector<void*> bufs((size_t)n);
+  // Measured on 2 x B200 (NV18), C3 1024^2 x 256 spp (gpurun call AA): peer 42.5 ms + 1.4 ms of enqueue, nccl 42.2 + 0.6 + 0.6 --
+  // a 16 MiB ncclReduce costs < 0.1 ms next to a 42 ms (84 / N) render, and cudaMalloc of a peer-mapped image is slow
+  // (outliers of 50 ms when a renderer is built per trial).  The fused form is therefore opt-in, not the default.
+  const bool peer = n > 1 && g->peer_ok && g->reduce_mode == 1 && desc->fuse_tiles && n_tiles <= 65535u;
+  if (n > 1 && g->reduce_mode == 1 && !peer)
+    return gfail(g, "cvr_group_render_image: group_reduce=peer needs peer access and fuse_tiles");
+  if (peer) {
+    // ---- resolve fused with the sum: every member adds its share into ONE image on the first device (peer memory)
+    cudaSetDevice(g->devices[0]);
+    if (g->peer_image_px < image_px) {
+      cudaStreamSynchronize(g->members[0]->stream);
+      cudaFree(g->d_peer_image);
+      g->d_peer_image = nullptr, g->peer_image_px = 0;
+      cudaError_t e = cudaMalloc((void**)&g->d_peer_image, image_px * sizeof(float4));
+      if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[0], cudaGetErrorString(e));
+      g->peer_image_px = image_px;
+    }
+    for (int r = 0; r < n; ++r) bufs[(size_t)r] = g->d_peer_image;
+    cudaError_t e = cudaMemsetAsync(g->d_peer_image, 0, image_px * sizeof(float4), g->members[0]->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(g->ev_zero, g->members[0]->stream);
+    if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[0], cudaGetErrorString(e));
+    if (int bad = for_each_member(g, [&](int r) {
+          cvr_handle m = g->members[(size_t)r];
+          if (set_device(m)) return 1;
+          // nobody adds before the image is zero; the adds are ordered behind this member's own render by its stream
+          if (r > 0 && cudaStreamWaitEvent(m->stream, g->ev_zero, 0) != cudaSuccess) return fail(m, "cudaStreamWaitEvent failed");
+          RenderPhase ph[2];
+          const int np = phases_of(r, ph);
+          if (render_phases(m, desc, ph, np, nullptr, g->d_peer_image, false, false, true)) return 1;
+          if (cudaEventRecord(g->ev_done[(size_t)r], m->stream) != cudaSuccess) return fail(m, "cudaEventRecord failed");
+          return 0;
+        }))
+      return member_failed(g, bad, "cvr_group_render_image");
+    pt.mark("renders enqueued");
+    cudaSetDevice(g->devices[0]);
+    for (int r = 1; r < n; ++r)
+      if (cudaStreamWaitEvent(g->members[0]->stream, g->ev_done[(size_t)r], 0) != cudaSuccess)
+        return gfail(g, "cvr_group_render_image: cudaStreamWaitEvent failed");
+  } else {
+    if (g->image_px < image_px) {
+      for (int r = 0; r < n; ++r) {
+        cudaSetDevice(g->devices[(size_t)r]);
+        if (g->d_images[(size_t)r]) cudaFreeAsync(g->d_images[(size_t)r], g->members[(size_t)r]->stream);
+        g->d_images[(size_t)r] = nullptr;
+        cudaError_t e = cudaMallocAsync((void**)&g->d_images[(size_t)r], image_px * sizeof(float4), g->members[(size_t)r]->stream);
+        if (e != cudaSuccess) {
+          g->image_px = 0;
+          return gfail(g, "cvr_group_render_image: device %d: %s", g->devices[(size_t)r], cudaGetErrorString(e));
+        }
+      }
+      g->image_px = image_px;
+    }
+    for (int r = 0; r < n; ++r) bufs[(size_t)r] = g->d_images[(size_t)r];
+    if (d_image_rank0_out) bufs[0] = d_image_rank0_out;
+    // every rank renders its share into its own zeroed full-resolution image (one host thread each)
+    if (int bad = for_each_member(g, [&](int r) {
+          RenderPhase ph[2];
+          const int np = phases_of(r, ph);
+          // no sync here: the reduce is queued behind the render on the member's stream
+          return render_phases(g->members[(size_t)r], desc, ph, np, nullptr, bufs[(size_t)r], true, false);
+        }))
+      return member_failed(g, bad, "cvr_group_render_image");
+    pt.mark("renders enqueued");
+    if (n > 1 && cvr_group_reduce(g, bufs.data(), (uint64_t)image_px * 4)) return 1;
+  }
   if (n > 1) {
-    if (cvr_group_reduce(g, bufs.data(), (uint64_t)image_px * 4)) return 1;
-    pt.mark("renders + reduce done");
+    if (!peer) pt.mark("renders + reduce done");
     // alpha is "some path escaped" / iterations, not a sum over the ranks that saw one (k_clamp_alpha)
     cudaSetDevice(g->devices[0]);
     k_clamp_alpha<<<g->members[0]->sm_count * 4, 256, 0, g->members[0]->stream>>>((float4*)bufs[0], image_px,
                                                                                    1.0f / (float)desc->iterations);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && peer && d_image_rank0_out)  // the caller's buffer need not be peer-mapped: hand the sum over on device 0
+      e = cudaMemcpyAsync(d_image_rank0_out, g->d_peer_image, image_px * sizeof(float4), cudaMemcpyDeviceToDevice, g->members[0]->stream);
     if (e != cudaSuccess) return gfail(g, "cvr_group_render_image: alpha: %s", cudaGetErrorString(e));
   }
   if (host_image) {

@@ -1936,6 +1936,11 @@ __global__ void k_resolve_tile(const float4* __restrict__ tile, uint32_t tile_w,
 struct ResolveOwner {
   uint32_t n, first[2], stride[2], limit[2];
 };
+// ADD = the resolve fused with the cross-device sum: instead of storing into its own image, every device of a group ADDS
+// its resolved share straight into the FIRST device's image through NVLink peer memory -- one 16-byte
+// `red.relaxed.sys.global.add.v4.f32` per pixel (SASS REDG.E.ADD.F32x4...SYS), fire and forget.  No per-device
+// full-resolution image, no zero fill of it, no collective call: the sum happens in the first device's L2.
+template <bool ADD>
 __global__ void k_resolve_tiles(const float4* __restrict__ accum, uint32_t tile_w, uint32_t tile_h, uint32_t full_w,
                                 const uint2* __restrict__ origins, float4* __restrict__ image, float scale, ResolveOwner own) {
   const uint32_t k = blockIdx.y;
@@ -1950,7 +1955,11 @@ __global__ void k_resolve_tiles(const float4* __restrict__ accum, uint32_t tile_
     const size_t at = (size_t)(y + o.y) * full_w + (x + o.x);
     float4 v = accum[at];
     v.x = v.x / scale, v.y = v.y / scale, v.z = v.z / scale, v.w = v.w / scale;
-    image[at] = v;
+    if (ADD)
+      asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(image + at), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    else
+      image[at] = v;
   }
 }
 

@@ -68,6 +68,7 @@ struct cvr_renderer {
   int fix_nan = 0;
   int exit_others = 16;  // KernelParams::exit_others
   size_t l2_fetch_saved = 0;  // the device's L2 fetch granularity before option "l2_fetch" changed it (0 = untouched)
+  int regen_block = 0;  // regen_order=block: path ids walk 8 x 4 pixel blocks (statistical parity; measured: no gain)
   int skip = -1;  // fetch-skip table (cvr_kernels.cuh: SkipTab): -1 = auto (on where it applies), 0, 1
 
   // launcher state
@@ -567,6 +568,8 @@ int launch(cvr_handle h, float4* out, uint32_t out_stride, int out_full, const u
   P.fix_nan = h->fix_nan;
   P.policy = h->policy;
   P.exit_others = h->exit_others;
+  // the block order needs whole 8 x 4 blocks; any other tile shape keeps the row order
+  P.regen_block = (h->regen_block && h->tile_w % 8u == 0 && h->tile_h % 4u == 0) ? 1u : 0u;
   P.pair = effective_pair(h);
   P.rr = h->rr;
   P.pullback = (h->variant != VAR_REGEN) ? 1 : 0;
@@ -805,6 +808,9 @@ int cvr_set_option(cvr_handle h, const char* key, const char* value) {
     h->pair = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
   } else if (k == "exit_others") {
     h->exit_others = atoi(value);
+  } else if (k == "regen_order") {
+    if (v != "row" && v != "block") return fail(h, "regen_order: unknown value '%s' (row | block)", value);
+    h->regen_block = v == "block" ? 1 : 0;
   } else if (k == "skip") {
     h->skip = v == "auto" ? -1 : (atoi(value) ? 1 : 0);
     h->inited = false;
@@ -882,6 +888,8 @@ int cvr_get_option(cvr_handle h, const char* key, char* value, size_t cap) {
     v = std::to_string(effective_pair(h));
   else if (k == "exit_others")
     v = std::to_string(h->exit_others);
+  else if (k == "regen_order")
+    v = h->regen_block ? "block" : "row";
   else if (k == "skip")  // "0" or the brick edge in cells the table was planned with (after the first launch / init)
     v = h->skip_bytes ? std::to_string(1u << h->skip_shift) : std::string(skip_wanted(h) && !h->inited ? "auto" : "0");
   else if (k == "warp_slots")

@@ -96,7 +96,8 @@ struct KernelParams {
   // fetch-skip table (warp scheduler, fused arithmetic, global majorant; see SkipTab below)
   const uint8_t* skip_tab;  // one byte per brick of (1 << skip_shift)^3 lookup cells, x fastest
   uint32_t skip_n;          // bytes in the table (0 = feature off)
-  uint32_t skip_shift, skip_bx, skip_bxy;  // brick edge = 1 << shift cells; row / slice strides in bricks
+  uint32_t skip_shift, skip_bx, skip_bxy;
+  uint32_t regen_block;  // 1: path ids walk 8 x 4 pixel blocks of the tile (regen_order=block)  // brick edge = 1 << shift cells; row / slice strides in bricks
 };
 
 // S_BOUNDARY_P = boundary event whose FIRST uniform is already drawn and parked in
@@ -515,6 +516,14 @@ CVR_DEV void start_path(const KernelParams& P, unsigned long long g, unsigned lo
   if (RNGM == RNG_XORWOW_PATH) R.rng.init((int32_t)(seed_k + (uint32_t)path_id));
   if (RNGM == RNG_PHILOX) R.rng.init((unsigned long long)seed_k + path_id);
   uint32_t image_id = (uint32_t)(path_id % P.npix);
+  if (P.regen_block) {
+    // regen_order=block (experiment, section 3.6 of DESIGN.md): consecutive path ids walk 8 x 4 pixel blocks instead of
+    // rows, so the 32 paths a warp regenerates at once start on a compact patch of the image -- the 2-D analogue of the
+    // reference's Morton-ordered regeneration.  A bijection on the tile's pixels (tile_w % 8 == 0, tile_h % 4 == 0 checked
+    // by the host); which pixel a stream lands on changes, so parity of this mode is statistical.
+    const uint32_t bw = P.tile_w >> 3, blk = image_id >> 5, in = image_id & 31u;
+    image_id = ((blk / bw) * 4u + (in >> 3)) * P.tile_w + (blk % bw) * 8u + (in & 7u);
+  }
   float u0 = R.rng.next();
   float u1 = R.rng.next();
   camera_ray(P.cam, image_id, off_x, off_y, u0, u1, R.o, R.d);

@@ -153,6 +153,7 @@ SYMBOLS = [
     ("cvr_trace_paths_logged", C.c_int, [H, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]),
     ("cvr_rng_kat", C.c_int, [H, C.POINTER(C.c_int32), C.c_int, C.c_int, u32p, f32p]),
     ("cvr_debug_lookup", C.c_int, [H, f32p, C.c_int, f32p, f32p]),
+    ("cvr_debug_trig_check", C.c_int, [H, C.c_float, C.POINTER(C.c_uint64), u32p]),
     ("cvr_gather_roofline", C.c_int, [H, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("cvr_synth_volume", C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, f32p, f32p, f32p]),
     ("cvr_set_scene_sparse", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -2177,6 +2177,33 @@ int cvr_rng_kat(cvr_handle h, const int32_t* seeds, int n_seeds, int n, uint32_t
   return 0;
 }
 
+int cvr_debug_trig_check(cvr_handle h, float limit, uint64_t mismatches[3], uint32_t first_bad_bits[3]) {
+  CVR_CHECK_HANDLE(h);
+  if (!mismatches || !(limit > 0.f) || !(limit < 105615.0f)) return fail(h, "cvr_debug_trig_check: bad arguments (0 < limit < 105615)");
+  if (set_device(h)) return 1;
+  unsigned long long* d_m;
+  uint32_t* d_f;
+  CVR_CUDA(h, cudaMalloc(&d_m, 3 * sizeof(unsigned long long)));
+  CVR_CUDA(h, cudaMalloc(&d_f, 3 * sizeof(uint32_t)));
+  CVR_CUDA(h, cudaMemsetAsync(d_m, 0, 3 * sizeof(unsigned long long), h->stream));
+  CVR_CUDA(h, cudaMemsetAsync(d_f, 0xff, 3 * sizeof(uint32_t), h->stream));
+  uint32_t limit_bits;
+  std::memcpy(&limit_bits, &limit, 4);
+  k_trig_check<<<h->sm_count * 16, 256, 0, h->stream>>>(limit_bits, d_m, d_f);
+  CVR_CUDA(h, cudaGetLastError());
+  unsigned long long m[3];
+  uint32_t f[3];
+  CVR_CUDA(h, cudaMemcpyAsync(m, d_m, sizeof m, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaMemcpyAsync(f, d_f, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+  CVR_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_m), cudaFree(d_f);
+  for (int i = 0; i < 3; ++i) {
+    mismatches[i] = m[i];
+    if (first_bad_bits) first_bad_bits[i] = f[i];
+  }
+  return 0;
+}
+
 int cvr_gather_roofline(cvr_handle h, uint64_t footprint_bytes, int loads_per_thread, int unroll, double* gbs) {
   CVR_CHECK_HANDLE(h);
   if (!gbs || footprint_bytes < 4096 || loads_per_thread < 1) return fail(h, "cvr_gather_roofline: bad arguments");

@@ -469,8 +469,30 @@ CVR_DEV bool ggx_sample_fast(float ax, float ay, float eta, V3 wi, RNG& rng, V3&
   return true;
 }
 
+// ---- cold code out of line ----------------------------------------------------------------------
+// The fused kernels are ~54 KB of SASS against a 32 KB L1.5 instruction cache (and ~6 KB of L0 per scheduler), and 28
+// warps per SM sit in different parts of it: ncu shows 0.3 (hetvol) ... 1.2 (manix) warps per issue stalled on
+// `no_instruction`.  Code that never runs in the reference's configurations is therefore kept OUT of the instruction
+// stream of the events (`__noinline__`: a call instead of 229 / 475 inlined instructions).  Measured on B200 (1024^2 x
+// 32 spp, kernel ms, gpurun calls AC / AD, profiles/r2_code_layout_ab.txt):
+//   anisotropic Henyey-Greenstein (g != 0; the reference's media are g == 0, Q5) out of line, every kernel:
+//     bucky 5.75 -> 5.42, hetvol 26.75 -> 26.33, manix 11.87 -> 11.36, fBm 512^3 20.65 -> 19.79, fBm 1024^3 20.72 -> 19.89,
+//     sparse 1024^3 12.94 -> 12.78 (-1 ... -6 %);
+//   the counter flush at kernel exit (70 shuffles) out of line as well: manix -> 10.92, fBm -> 19.28 / 19.48, sparse ->
+//     12.50 (-3 ... -8 % in total) but hetvol -> 27.23 (+2 %): only in the skip-table kernels (the ones that run volumes
+//     beyond the L2), which are the larger ones.
+// No arithmetic changes: every path stays bit-identical.  What does NOT work: an event that takes the path registers by
+// reference out of line (do_boundary, start_path: the whole PathRegs then lives in local memory, +18 ... +79 %).
+#ifndef CVR_COLD_NOINLINE
+#define CVR_COLD_NOINLINE 1
+#endif
+#if CVR_COLD_NOINLINE
+__device__ __noinline__ V3 hg_sample_cold(V3 dir, float g, float e1, float e2) { return hg_sample(dir, g, e1, e2); }
+#else
+CVR_DEV V3 hg_sample_cold(V3 dir, float g, float e1, float e2) { return hg_sample(dir, g, e1, e2); }
+#endif
 CVR_DEV V3 hg_sample_fast(V3 dir, float g, float e1, float e2) {
-  if (fabsf(g) > CVR_EPS) return hg_sample(dir, g, e1, e2);  // anisotropic phase: exact path
+  if (fabsf(g) > CVR_EPS) return hg_sample_cold(dir, g, e1, e2);  // anisotropic phase: exact path
   float cos_theta = 1.0f - 2.0f * e1;
   float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
   float sp, cp;
@@ -918,7 +940,7 @@ CVR_DEV void do_scatter(const KernelParams& P, PathRegs<Rng>& R, LaneCounters& C
 }
 
 // ---- boundary event (A10): NaiveVolPTsk_kernel.cuh:50-65 ----
-template <bool FAST = false, bool LOG = false, class Rng>
+template <bool FAST = false, bool LOG = false, bool SMALLTRIG = false, class Rng>
 CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
   // S_BOUNDARY_P: the first uniform of this event was drawn by the tracking loop (parked in t)
   StashRng<Rng> rng{R.rng, R.t, R.state == S_BOUNDARY_P};
@@ -940,7 +962,7 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
 #if CVR_FAST_GGX
     if (ggx_sample_fast(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
 #else
-    if (ggx_sample(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
+    if (ggx_sample<SMALLTRIG>(P.med.alpha_x, P.med.alpha_y, P.med.eta, dir, rng, R.d, weight)) {
 #endif
       ev_code |= EVF_OK | (R.d.z < 0.f ? EVF_WO_NEG : 0u);
       R.thr_x *= weight, R.thr_y *= weight, R.thr_z *= weight;
@@ -973,9 +995,7 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
   if (rng.has) R.rng.undo();
 }
 
-template <bool COUNT>
-CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lane) {
-  if (!COUNT) return;
+CVR_DEV void flush_counters_body(const KernelParams& P, LaneCounters& C, unsigned lane) {
   const unsigned FULL = 0xffffffffu;
   C.dens += C.pairs + C.cont;
   C.spec += C.pairs - C.cont;
@@ -997,6 +1017,18 @@ CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lan
     if (C.spec) atomicAdd(&P.ctr->speculative, (unsigned long long)C.spec);
     if (C.skip) atomicAdd(&P.ctr->skipped, (unsigned long long)C.skip);
   }
+}
+__device__ __noinline__ void flush_counters_outline(const KernelParams& P, LaneCounters& C, unsigned lane) {
+  flush_counters_body(P, C, lane);
+}
+// OUTLINE: a call instead of the inlined body (the skip-table kernels; "cold code out of line" above)
+template <bool COUNT, bool OUTLINE = false>
+CVR_DEV void flush_counters(const KernelParams& P, LaneCounters& C, unsigned lane) {
+  if (!COUNT) return;
+  if (OUTLINE && CVR_COLD_NOINLINE)
+    flush_counters_outline(P, C, lane);
+  else
+    flush_counters_body(P, C, lane);
 }
 
 // claim path ids for the idle lanes of this warp with one 64-bit atomic
@@ -1730,7 +1762,7 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     } else if (key == 1) {
       if (have) do_scatter<LAYOUT, COUNT, FAST, LOG>(P, R, C);
     } else if (key == 2) {
-      if (have) do_boundary<FAST, LOG>(P, R);
+      if (have) do_boundary<FAST, LOG, SKIP>(P, R);  // SKIP: small-argument sin / cos (cvr_device.cuh)
     }
     if (have && R.state == S_ISECT) do_isect<COUNT, FAST, LOG>(P, R, C);
     // everything the tracking loop does not touch goes back to the slot now
@@ -1759,7 +1791,10 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
           need = max(min_lanes, 1);
           if (R.state == S_TRACK) track_pair_cb<LAYOUT, COUNT, SKIP>(P, I, G, R, C, ST);
         }
-      } else if (P.pair) {
+#ifndef CVR_SKIP_FORCE_PAIR
+#define CVR_SKIP_FORCE_PAIR 0
+#endif
+      } else if ((CVR_SKIP_FORCE_PAIR && SKIP) || P.pair) {
         // one test per iteration: stop below `need` tracking lanes; the first iteration runs with any.
         // (Two pairs per vote -- the census is 15 of the ~165 instructions of an iteration and runs
         // with all 32 lanes -- was measured and rejected: the coarser exit costs more than the votes,
@@ -1805,7 +1840,7 @@ __global__ void __launch_bounds__(SKIP ? CVR_WSKIP_BLOCK : CVR_WBLOCK, SKIP ? 1 
     for (int j = 0; j < K; ++j)
       if (st[j] == K_BUSY) st[j] = keys[lane + 32 * j];
   }
-  flush_counters<COUNT>(P, C, lane);
+  flush_counters<COUNT, SKIP>(P, C, lane);
 }
 
 // ---------------------------------------------------------------- layout builders
@@ -2038,6 +2073,31 @@ __global__ void __launch_bounds__(256) k_gather_bench(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------- debug kernels
+// parity hook: sin_small / cos_small / tan_small against libdevice's sinf / cosf / tanf on EVERY float of magnitude <= limit
+// (both signs) and on NaN; mismatch counts per function, the first mismatching bit pattern kept for the error message
+__global__ void k_trig_check(uint32_t limit_bits, unsigned long long* mismatches, uint32_t* first_bad) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  unsigned long long bad[3] = {0, 0, 0};
+  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m <= limit_bits + 1u; m += stride) {
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      const uint32_t bits = m > limit_bits ? (0x7FC00000u | (sgn << 31)) : (m | ((uint32_t)sgn << 31));  // last m: NaN
+      const float x = __uint_as_float(bits);
+      const float a[3] = {sin_small(x), cos_small(x), tan_small(x)};
+      const float b[3] = {sinf(x), cosf(x), tanf(x)};
+      for (int f = 0; f < 3; ++f) {
+        const bool same = __float_as_uint(a[f]) == __float_as_uint(b[f]) || (a[f] != a[f] && b[f] != b[f]);
+        if (!same) {
+          ++bad[f];
+          atomicMin(&first_bad[f], bits & 0x7FFFFFFFu);
+        }
+      }
+    }
+    if (m == 0xFFFFFFFFu) break;
+  }
+  for (int f = 0; f < 3; ++f)
+    if (bad[f]) atomicAdd(&mismatches[f], bad[f]);
+}
+
 __global__ void k_rng_kat(const int32_t* seeds, int n_seeds, int n, uint32_t* words, float* uni) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_seeds) return;

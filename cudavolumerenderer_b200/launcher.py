@@ -343,6 +343,13 @@ class VolPTKernelLauncher:
         """tracePaths plus the per-path event log (DEVICE uint2[count * log_cap], include/cvr_abi.h)."""
         self._ck(self._lib.cvr_trace_paths_logged(self._h, first, count, d_per_path, d_log, log_cap), "tracePathsLogged")
 
+    def trigCheck(self, limit: float = 8.0):
+        """cvr_debug_trig_check: (mismatch counts of sin / cos / tan, first differing |x| bit patterns)."""
+        m = (C.c_uint64 * 3)()
+        f = (C.c_uint32 * 3)()
+        self._ck(self._lib.cvr_debug_trig_check(self._h, limit, m, f), "trigCheck")
+        return [int(v) for v in m], [int(v) for v in f]
+
     def rngKat(self, seeds, n: int):
         seeds = np.ascontiguousarray(seeds, np.int32)
         w = np.zeros((len(seeds), n), np.uint32)

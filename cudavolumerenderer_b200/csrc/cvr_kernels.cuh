@@ -952,10 +952,13 @@ CVR_DEV void do_boundary(const KernelParams& P, PathRegs<Rng>& R) {
     const V3 dir = frame_to_local(R.ncode, normalize(v3(-R.d.x, -R.d.y, -R.d.z)));
     R.o = v3(fmaf(R.d.x, R.dist, R.o.x), fmaf(R.d.y, R.dist, R.o.y), fmaf(R.d.z, R.dist, R.o.z));
     // the sampler writes the LOCAL direction into the ray even when it then fails
-    // CVR_FAST_GGX=1 swaps in the sampler without the angle round trip (ggx_sample_vndf_fast).
-    // Measured, 1024^2 x 64 spp, Msamples/s off / on: bucky 5815 / 6585 (boundary-dominated),
-    // but hetvol 1026 / 1009, manix 2620 / 2530, fbm 512^3 1130 / 1090 -- the hot loop's SASS is
-    // unchanged, the kernel is 550 instructions shorter, and yet it is slower; left off.
+    // CVR_FAST_GGX=1 swaps in the sampler without the angle round trip (ggx_sample_vndf_fast).  It CHANGES the
+    // sampler's arithmetic (the reference's acos / atan2 / tan round trip amplifies one ulp of a nearly axial
+    // direction to 6e-4 of the angle, so per-path agreement with the reference would drop on boundary-dominated
+    // scenes), which is why it stays off: the fused mode keeps the GGX boundary in the reference's form.
+    // Measured as a code-size experiment in round 2 (kernel ms at 1024^2 x 32 spp, profiles/r2_code_layout_ab.txt):
+    // bucky 5.75 -> 4.93, manix 11.83 -> 10.60, fBm 1024^3 20.71 -> 19.40, hetvol 26.77 -> 26.64; most of that gain is
+    // now had without touching the arithmetic ("cold code out of line" above and sin_small / cos_small).
 #ifndef CVR_FAST_GGX
 #define CVR_FAST_GGX 0
 #endif

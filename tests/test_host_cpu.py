@@ -131,11 +131,22 @@ def test_xml_vol_loader_reproduces_reference_quirks(cli, tmp_path):
     # albedo alpha = 1 per voxel
     assert abs(float(d["sums"][1]) - (float(alb.astype(np.float64).sum()) + 5 * 6 * 7)) < 1e-2
     assert "Auto-detected scene type: MitsubaXml" in out
+    # the same file through the C ABI (cvr_scene_file_load) = what the ctypes layer hands to cvr_set_scene: same loader, same quirks
+    from cudavolumerenderer_b200 import abi, scenes
+
+    sc = scenes.load(str(tmp_path / "scene.xml"))
+    assert sc.density.shape == (5, 6, 7) and sc.albedo.shape == (5, 6, 7, 4)
+    assert np.array_equal(sc.density, den) and np.array_equal(sc.albedo[..., :3], alb) and np.all(sc.albedo[..., 3] == 1.0)
+    assert np.allclose(sc.box_min + sc.box_max, [-0.64, -0.64, -0.25, 0.64, 0.64, 0.25]) and sc.scale == 800.0 and sc.max_density == 1.0
+    info = abi.load_scene_file(str(tmp_path / "scene.xml"), "MitsubaXml")
+    assert info["type"] == "MitsubaXml" and abs(info["fov_x"] - 0.33) < 1e-6
     bad = tmp_path / "bad.vol"
     bad.write_bytes(b"XXX" + b"\0" * 64)
     (tmp_path / "bad.xml").write_text((tmp_path / "scene.xml").read_text().replace("smoke.vol", "bad.vol"))
     rc, out, err = run(cli, str(tmp_path / "bad.xml"), "--dump-scene")
     assert rc == 1 and "incorrect header identifier" in err
+    with pytest.raises(abi.CvrError, match="incorrect header identifier"):
+        scenes.load(str(tmp_path / "bad.xml"))
 
 
 def test_cli_flags_and_error_paths(cli, tmp_path):

@@ -40,7 +40,7 @@ for key in which:
     kl.setStream(stream.cuda_stream)
     kl.setScene(sc)
     d_img = torch.zeros((res, res, 4), dtype=torch.float32, device=dev)
-    for mode in ("tiles", "spp"):
+    for mode in ("tiles", "spp", "balanced"):
         def step():
             kl.setSeed(0)
             render_sharded(kl, (res, res), tiles, spp, mode, d_img, fov_x=sc.fov_x)

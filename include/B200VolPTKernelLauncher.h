@@ -8,7 +8,7 @@
  *
  * It needs the reference's headers and is therefore NOT part of the product build;
  * oracle/ref_binding_check.cpp compiles it against /root/reference and runs that call sequence
- * (oracle/Makefile target `ref_binding`, tests/test_oracle.py::test_reference_side_binding_compiles_and_runs).
+ * (oracle/Makefile target `ref_binding`, tests/test_oracle.py::test_reference_side_binding_compiles_and_links, tests/test_gpu_parity.py::test_reference_tile_driver_runs_on_the_documented_binding).
  */
 #pragma once
 #include <cstdio>

@@ -480,7 +480,10 @@ CVR_DEV bool ggx_sample_fast(float ax, float ay, float eta, V3 wi, RNG& rng, V3&
 //     sparse 1024^3 12.94 -> 12.78 (-1 ... -6 %);
 //   the counter flush at kernel exit (70 shuffles) out of line as well: manix -> 10.92, fBm -> 19.28 / 19.48, sparse ->
 //     12.50 (-3 ... -8 % in total) but hetvol -> 27.23 (+2 %): only in the skip-table kernels (the ones that run volumes
-//     beyond the L2), which are the larger ones.
+//     beyond the L2).  Besides the code moved, the call changes where the lane counters live: their address escapes, so
+//     they stay in LOCAL memory between rounds (52 LDL / STL in the kernel, none inside the pair loop: ptxas loads them
+//     into registers around it), which frees registers in the event code.  The skip-table kernels have the L1 data pipe to
+//     spare for that (~50 % busy); hetvol's kernel does not (84 %).
 // No arithmetic changes: every path stays bit-identical.  What does NOT work: an event that takes the path registers by
 // reference out of line (do_boundary, start_path: the whole PathRegs then lives in local memory, +18 ... +79 %).
 #ifndef CVR_COLD_NOINLINE
